@@ -1,0 +1,119 @@
+/*
+ * ns_coder.h -- C ABI of the B200-native steganographic coder step.
+ *
+ * The reference (nobkagit/NeuralSteganography) is pure Python and has no FFI;
+ * its boundary for this path is the Python LMProvider protocol
+ * (src/neuralstego/api.py:42-56).  This header is the native boundary a
+ * maintainer binds with ctypes (INTEGRATION.md shows the stub): plain
+ * pointers and sizes, no torch types.  Every entry point
+ *   - takes DEVICE pointers (unless the name ends in _host) and a cudaStream_t
+ *     passed as void*,
+ *   - never allocates, never synchronises, is CUDA-graph capturable,
+ *   - returns 0 on success, a negative NS_E_* code for argument errors, or a
+ *     positive cudaError_t.
+ *
+ * One "stream" is one independent message/cover pair (one chunk of
+ * stego_encode, api.py:736-747).  All per-stream arrays have B entries.
+ */
+#ifndef NS_CODER_H
+#define NS_CODER_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NS_ABI_VERSION 1
+
+/* error codes */
+#define NS_OK 0
+#define NS_E_NULL (-1)        /* required pointer is NULL */
+#define NS_E_RANGE (-2)       /* precision/topk/temp/B/V out of range */
+#define NS_E_VOCAB (-3)       /* vocabulary does not fit the kernel's shared-memory row */
+#define NS_E_ALIGN (-4)       /* pointer not 4-byte aligned */
+#define NS_E_NODEVICE (-5)    /* no sm_100 device / kernel image missing */
+
+/* per-stream phase (uint8) */
+#define NS_PHASE_CODING 0     /* message bits remain: full arithmetic step            */
+#define NS_PHASE_TAIL 1       /* finish_sent tail: emit rank-0 token, no interval update
+                                 (code_base/arithmetic.py:135-137)                    */
+#define NS_PHASE_DONE 2       /* stream finished: kernel leaves it untouched          */
+
+/* per-stream status bits written by the kernels (int32, OR-ed, 0 = fine) */
+#define NS_ST_OUT_OF_RANGE 1  /* decode: observed token is not in the kept set (rank >= k,
+                                 code_base/arithmetic.py:301) -- coded as rank 0 like :342 */
+#define NS_ST_BIN_OVERFLOW 2  /* selection bucket exceeded the resolve capacity (degenerate
+                                 logits, e.g. thousands of exactly equal values)       */
+#define NS_ST_EST_RETRY 4     /* provisional normaliser was outside its guard band; the row
+                                 was recomputed with the exact one (informational)     */
+#define NS_ST_TOKEN_OVERFLOW 8 /* encode: token buffer full (ntok >= token_cap); stream stopped */
+
+/* Arithmetic coder (A): code_base/arithmetic.py:78-217 (encode), :220-373 (decode). */
+typedef struct ns_ac_params {
+  /* logits: fp32 [B, V], row r at logits + r*ld (elements).  Read-only: the
+     reference's in-place masking (arithmetic.py:124-125) is applied on chip. */
+  const float* logits;
+  int64_t ld;
+  int32_t B;
+  int32_t V;
+  double temp;          /* arithmetic.py:85,129  */
+  int32_t precision;    /* arithmetic.py:86,96   (1..48) */
+  int32_t topk;         /* arithmetic.py:87,142  */
+  int32_t mask_id[2];   /* forbidden token ids (arithmetic.py:124-125: V-1 and 628); -1 = none */
+  /* coder state, arithmetic.py:98: cur_interval = [lo, hi) */
+  uint64_t* lo;
+  uint64_t* hi;
+  uint8_t* phase;       /* NS_PHASE_*; may be NULL (= all coding) */
+  int32_t* status;      /* NS_ST_* bits, OR-ed in; may be NULL */
+  /* Per-stream token counter.  When non-NULL the step reads/writes token slot
+     ntok[r] of its stream and increments it, so the same parameter block (and a
+     captured CUDA graph) serves every step of the generation loop; when NULL the
+     slot is 0.  Encode stops a stream whose counter reaches token_cap; decode
+     marks a stream DONE when the counter reaches ntok_total[r] and treats its
+     last token as arithmetic.py:356 does. */
+  int32_t* ntok;
+  int32_t token_cap;
+  const int32_t* ntok_total;
+  /* ---- encode only ---------------------------------------------------- */
+  /* message bits packed MSB-first: bit t of stream r is
+     (msg[r*msg_stride + (t>>5)] >> (31 - (t&31))) & 1   (arithmetic.py:168-171) */
+  const uint32_t* msg;
+  int64_t msg_stride;   /* words per stream */
+  const int32_t* msg_len;   /* bits per stream */
+  int32_t* cursor;      /* "i" of arithmetic.py:112,184 */
+  int32_t* token_out;   /* token chosen this step: token_out[r*token_stride + slot] */
+  int64_t token_stride;
+  int32_t finish_sent;  /* arithmetic.py:83,114 */
+  const uint8_t* sent_end;  /* [V] 1 if the token text contains . ! ? (utils.py:55-57); may be NULL */
+  /* ---- decode only ---------------------------------------------------- */
+  const int32_t* token_in;  /* observed token: token_in[r*token_stride + slot] */
+  const uint8_t* is_last;   /* [B] 1 on the stream's last token (arithmetic.py:356); may be NULL;
+                               ignored when ntok_total is given */
+  uint32_t* out_bits;   /* recovered bits, packed MSB-first like msg */
+  int64_t out_stride;   /* words per stream */
+  int32_t* out_len;     /* bits written so far per stream */
+  /* ---- both ----------------------------------------------------------- */
+  uint8_t* nbits_out;   /* bits consumed/emitted this step (arithmetic.py:183); may be NULL */
+  /* optional per-step trace for parity tests: [B,4] = new_bottom, new_top, k, selection-mass */
+  uint64_t* trace;
+} ns_ac_params;
+
+int ns_version(void);
+const char* ns_last_error_string(void);
+/* largest V the arithmetic-coder kernels accept on this build */
+int ns_ac_max_vocab(void);
+
+/* one encode step for B streams (code_base/arithmetic.py:114-210 loop body) */
+int ns_ac_encode_step(const ns_ac_params* p, void* cuda_stream);
+/* one decode step for B streams (code_base/arithmetic.py:255-371 loop body) */
+int ns_ac_decode_step(const ns_ac_params* p, void* cuda_stream);
+/* parity-test helper: integer bin widths of the kept set per token id,
+   q_out [B,V] uint64 (0 = not kept), meta_out [B,4] = k, slack, total, range.
+   (code_base/arithmetic.py:146-158) */
+int ns_ac_debug_bins(const ns_ac_params* p, uint64_t* q_out, uint64_t* meta_out, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NS_CODER_H */

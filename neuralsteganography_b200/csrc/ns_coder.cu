@@ -1,0 +1,594 @@
+// ns_coder.cu -- arithmetic-coder step (A) for B independent streams, sm_100a.
+//
+// Reference behaviour: code_base/arithmetic.py:114-210 (encode loop body) and
+// :255-371 (decode loop body); exact step specification in SURVEY.md section 8a.1.
+// One CTA owns one stream: the V-wide fp32 logits row lives in shared memory and is
+// never sorted.  The reference's "sort, softmax, cut, round, cumsum, search" becomes
+//   P1  fp64 exp of every element, fixed-order sum            (softmax normaliser, :130)
+//   P2  kept set: p_i >= 1/range, clamped to [2, topk]        (:140-142)
+//   P3  integer bin widths q_i = rint(e_i * range / S_kept)   (:146-149), total mass,
+//       mass histogram over 2048 monotone key buckets          (replaces :127 + :150)
+//   SEL prefix over buckets -> bucket holding the target -> collect that bucket ->
+//       exact rank inside it                                   (:153-155 overfill, :172 search)
+//   UPD shared-prefix bits + interval rescale                  (:175-190)
+// See DESIGN.md for the data layout, the floating-point contract and the roofline.
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ns_coder.h"
+#include "ns_math.cuh"
+
+namespace {
+
+typedef unsigned long long u64;
+
+constexpr int NT = 1024;             // threads per CTA
+constexpr int NWARPS = NT / 32;
+constexpr int LIST_CAP = 512;        // resolve capacity of one selection bucket
+constexpr int HIST_BYTES = 8192;     // 2048 x u32 (precision <= 31) or 1024 x u64
+constexpr int SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA on sm_100
+
+struct ListEntry {
+  u64 pack;   // (orderable key << 32) | ~id : larger = earlier in the coder's order
+  u64 w;      // weight (mass or count)
+};
+
+struct Scalars {
+  u64 red[NWARPS];       // reduction scratch
+  int list_count;
+  int sel_bin;
+  u64 sel_prefix;
+  int res_idx;
+  u64 res_before;
+  u64 res_w;
+  int res_found;
+};
+
+constexpr int FIXED_BYTES = NS_EXP_N * 8 + HIST_BYTES + LIST_CAP * (int)sizeof(ListEntry) + 1024;
+static_assert(sizeof(Scalars) <= 1024, "scalar block too large");
+constexpr int MAX_VOCAB = (SMEM_LIMIT - FIXED_BYTES) / 4 - 8;
+
+__constant__ double c_exp_tab[NS_EXP_N] = {NS_EXP_TAB_VALUES};
+
+// ------------------------------------------------------------------------------------
+// block-wide reductions, bit-deterministic: xor-butterfly inside the warp (commutative,
+// so every lane holds the same bits), then warp partials combined in index order.
+// ------------------------------------------------------------------------------------
+struct OpAddD { __device__ double operator()(double a, double b) const { return a + b; } };
+struct OpAddU { __device__ u64 operator()(u64 a, u64 b) const { return a + b; } };
+struct OpMaxU { __device__ u64 operator()(u64 a, u64 b) const { return a > b ? a : b; } };
+struct OpMinU { __device__ u64 operator()(u64 a, u64 b) const { return a < b ? a : b; } };
+
+template <class Op>
+__device__ __forceinline__ u64 block_reduce_u(u64 v, Op op, u64* scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  u64 r = scratch[0];
+#pragma unroll 1
+  for (int w = 1; w < NWARPS; ++w) r = op(r, scratch[w]);
+  return r;
+}
+
+__device__ __forceinline__ double block_sum_d(double v, u64* scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = (u64)__double_as_longlong(v);
+  __syncthreads();
+  double r = __longlong_as_double((long long)scratch[0]);
+#pragma unroll 1
+  for (int w = 1; w < NWARPS; ++w) r = r + __longlong_as_double((long long)scratch[w]);
+  return r;
+}
+
+__device__ __forceinline__ u64 pack_of(float key, int id) {
+  return ((u64)ns_f32_orderable(key) << 32) | (u64)(0xFFFFFFFFu - (uint32_t)id);
+}
+__device__ __forceinline__ float key_of_pack(u64 p) {
+  uint32_t u = (uint32_t)(p >> 32);
+  uint32_t bits = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+  return __uint_as_float(bits);
+}
+__device__ __forceinline__ int id_of_pack(u64 p) { return (int)(0xFFFFFFFFu - (uint32_t)p); }
+
+__device__ __forceinline__ int bin_of(float key, float m, float scale, int nb) {
+  float d = (m - key) * scale;          // monotone non-increasing in key
+  d = fminf(d, (float)(nb - 1));
+  return (int)d;
+}
+
+// Everything a thread needs to turn a key into its exp / probability / bin width.
+struct RowMath {
+  const float* keys;
+  const double* tab;
+  int V;
+  float m;            // row maximum (fp32, exact)
+  double dm;          // double(m)/temp
+  double temp;
+  bool unit_temp;
+  double inv_sum;     // 1 / sum_i e_i                       (softmax, arithmetic.py:130)
+  double thr;         // 1 / range                           (:141)
+  bool rank_form;     // kept set = top-k0 by order instead of p >= thr
+  u64 bound_pack;     // last kept element in the coder's order
+  double C;           // range / sum_kept e_i                (:146)
+
+  // (double(x)/temp) - (double(m)/temp), the reference's operation order (:128-130).
+  __device__ __forceinline__ double a_of(float key) const {
+    double x = (double)key;
+    if (!unit_temp) x = __ddiv_rn(x, temp);
+    return x - dm;
+  }
+  __device__ __forceinline__ double e_of(float key) const { return ns_exp64_neg(a_of(key), tab); }
+  __device__ __forceinline__ bool kept(float key, int id, double e) const {
+    if (rank_form) return pack_of(key, id) >= bound_pack;
+    return (e * inv_sum) >= thr;
+  }
+  // integer bin width of element i, 0 when not kept (:146-149, round half to even)
+  __device__ __forceinline__ u64 mass(float key, int id) const {
+    if (rank_form && pack_of(key, id) < bound_pack) return 0;
+    double e = e_of(key);
+    if (!rank_form && !((e * inv_sum) >= thr)) return 0;
+    return (u64)__double2ll_rn(e * C);
+  }
+};
+
+// ------------------------------------------------------------------------------------
+// histogram selection: first position in the coder's order whose inclusive cumulative
+// weight exceeds tau.  The histogram has been filled by the caller.
+// ------------------------------------------------------------------------------------
+template <typename HistT, int NB>
+__device__ void sel_locate(const HistT* hist, u64 tau, Scalars* sc) {
+  constexpr int BPT = NB / NT;          // bins per thread (2 for u32, 1 for u64)
+  static_assert(BPT >= 1, "histogram smaller than the CTA");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  u64 local[BPT];
+  u64 tsum = 0;
+#pragma unroll
+  for (int b = 0; b < BPT; ++b) { local[b] = (u64)hist[tid * BPT + b]; tsum += local[b]; }
+  // inclusive scan over threads
+  u64 inc = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    u64 t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) sc->red[warp] = inc;
+  if (tid == 0) { sc->sel_bin = -1; sc->sel_prefix = 0; }
+  __syncthreads();
+  u64 woff = 0;
+#pragma unroll 1
+  for (int w = 0; w < warp; ++w) woff += sc->red[w];
+  u64 excl = woff + inc - tsum;
+#pragma unroll
+  for (int b = 0; b < BPT; ++b) {
+    if (local[b] != 0 && excl <= tau && tau < excl + local[b]) {
+      sc->sel_bin = tid * BPT + b;
+      sc->sel_prefix = excl;
+    }
+    excl += local[b];
+  }
+  __syncthreads();
+}
+
+// Exact resolution among the collected entries of the target bucket.
+__device__ void sel_resolve(const ListEntry* list, int n, u64 tau, u64 prefix, Scalars* sc) {
+  if (threadIdx.x == 0) sc->res_found = 0;
+  __syncthreads();
+  for (int c = threadIdx.x; c < n; c += NT) {
+    const u64 pc = list[c].pack, wc = list[c].w;
+    u64 before = prefix;
+    for (int o = 0; o < n; ++o) {
+      const u64 po = list[o].pack;
+      if (po > pc) before += list[o].w;
+    }
+    if (wc != 0 && before <= tau && tau < before + wc) {
+      sc->res_idx = id_of_pack(pc);
+      sc->res_before = before;
+      sc->res_w = wc;
+      sc->res_found = 1;
+    }
+  }
+  __syncthreads();
+}
+
+enum { MODE_ENC = 0, MODE_DEC = 1, MODE_DEBUG = 2 };
+
+template <int MODE, typename HistT>
+__global__ void __launch_bounds__(NT, 1) ac_step_kernel(ns_ac_params P, u64* dbg_q, u64* dbg_meta) {
+  constexpr int NB = HIST_BYTES / (int)sizeof(HistT);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* tab = reinterpret_cast<double*>(smem_raw);
+  HistT* hist = reinterpret_cast<HistT*>(smem_raw + NS_EXP_N * 8);
+  ListEntry* list = reinterpret_cast<ListEntry*>(smem_raw + NS_EXP_N * 8 + HIST_BYTES);
+  Scalars* sc = reinterpret_cast<Scalars*>(smem_raw + NS_EXP_N * 8 + HIST_BYTES + LIST_CAP * sizeof(ListEntry));
+  float* keys_base = reinterpret_cast<float*>(smem_raw + FIXED_BYTES);
+
+  const int row = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int V = P.V;
+  uint8_t phase = P.phase ? P.phase[row] : (uint8_t)NS_PHASE_CODING;
+  if (phase == NS_PHASE_DONE) return;
+  if (MODE != MODE_ENC) phase = NS_PHASE_CODING;
+  const int slot = P.ntok ? P.ntok[row] : 0;
+  if (MODE == MODE_ENC && P.ntok && slot >= P.token_cap) {
+    if (tid == 0) {
+      if (P.phase) P.phase[row] = NS_PHASE_DONE;
+      if (P.status) atomicOr(&P.status[row], NS_ST_TOKEN_OVERFLOW);
+    }
+    return;
+  }
+  if (MODE == MODE_DEC && P.ntok_total && slot >= P.ntok_total[row]) {
+    if (tid == 0 && P.phase) P.phase[row] = NS_PHASE_DONE;
+    return;
+  }
+
+  // ---- stage the row: 128-bit loads, shared copy keeps the global 16-byte phase --------
+  const float* g = P.logits + (size_t)row * (size_t)P.ld;
+  const int mis = (int)(((uintptr_t)g & 15u) >> 2);
+  float* keys = keys_base + mis;
+  {
+    int head = (4 - mis) & 3;
+    if (head > V) head = V;
+    if (tid < head) keys[tid] = g[tid] + 0.0f;               // +0.0f folds -0 into +0
+    const int nvec = (V - head) >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(g + head);
+    float4* s4 = reinterpret_cast<float4*>(keys + head);
+    for (int i = tid; i < nvec; i += NT) {
+      float4 v = __ldg(g4 + i);
+      v.x += 0.0f; v.y += 0.0f; v.z += 0.0f; v.w += 0.0f;
+      s4[i] = v;
+    }
+    const int done = head + (nvec << 2);
+    if (tid < V - done) keys[done + tid] = g[done + tid] + 0.0f;
+  }
+  for (int i = tid; i < NS_EXP_N; i += NT) tab[i] = c_exp_tab[i];
+  for (int i = tid; i < NB; i += NT) hist[i] = 0;
+  if (tid == 0) sc->list_count = 0;
+  __syncthreads();
+  // forbidden tokens (code_base/arithmetic.py:124-125 / :265-266): probability exactly 0
+  if (tid < 2) {
+    int id = P.mask_id[tid];
+    if (id >= 0 && id < V) keys[id] = -INFINITY;
+  }
+  __syncthreads();
+
+  // ---- row maximum (with lowest id among ties) and lowest finite key ---------------------
+  u64 pmax = 0, pmin = ~0ull;
+  for (int i = tid; i < V; i += NT) {
+    float k = keys[i];
+    u64 p = pack_of(k, i);
+    pmax = p > pmax ? p : pmax;
+    if (k > -INFINITY) pmin = p < pmin ? p : pmin;
+  }
+  pmax = block_reduce_u(pmax, OpMaxU(), sc->red);
+  pmin = block_reduce_u(pmin, OpMinU(), sc->red);
+  const float m = key_of_pack(pmax);
+  const int top_id = id_of_pack(pmax);
+
+  if (MODE == MODE_ENC && phase == NS_PHASE_TAIL) {
+    // finish_sent tail: rank-0 token, interval untouched (arithmetic.py:135-137)
+    if (tid == 0) {
+      P.token_out[(size_t)row * P.token_stride + slot] = top_id;
+      if (P.ntok) P.ntok[row] = slot + 1;
+      if (P.nbits_out) P.nbits_out[row] = 0;
+      if (P.phase && P.sent_end && P.sent_end[top_id]) P.phase[row] = NS_PHASE_DONE;
+    }
+    return;
+  }
+
+  const u64 lo = P.lo[row], hi = P.hi[row];
+  const u64 R = hi - lo;                                    // arithmetic.py:140
+
+  RowMath rm;
+  rm.keys = keys; rm.tab = tab; rm.V = V; rm.m = m; rm.temp = P.temp;
+  rm.unit_temp = (P.temp == 1.0);
+  rm.dm = rm.unit_temp ? (double)m : __ddiv_rn((double)m, P.temp);
+  rm.thr = __ddiv_rn(1.0, (double)R);                       // :141
+  rm.rank_form = false; rm.bound_pack = 0; rm.C = 0.0; rm.inv_sum = 0.0;
+
+  // ---- P1: softmax normaliser ------------------------------------------------------------
+  {
+    double acc0 = 0.0, acc1 = 0.0;
+    int i = tid;
+    for (; i + NT < V; i += 2 * NT) {
+      acc0 += rm.e_of(keys[i]);
+      acc1 += rm.e_of(keys[i + NT]);
+    }
+    if (i < V) acc0 += rm.e_of(keys[i]);
+    const double sum = block_sum_d(acc0 + acc1, sc->red);
+    rm.inv_sum = __ddiv_rn(1.0, sum);
+  }
+
+  // ---- P2: kept set -------------------------------------------------------------------------
+  u64 cand;
+  double S;
+  u64 bound = ~0ull;
+  {
+    u64 cnt = 0;
+    double acc = 0.0;
+    for (int i = tid; i < V; i += NT) {
+      const float k = keys[i];
+      const double e = rm.e_of(k);
+      if ((e * rm.inv_sum) >= rm.thr) {
+        cnt += 1;
+        acc += e;
+        u64 p = pack_of(k, i);
+        bound = p < bound ? p : bound;
+      }
+    }
+    cand = block_reduce_u(cnt, OpAddU(), sc->red);
+    bound = block_reduce_u(bound, OpMinU(), sc->red);
+    S = block_sum_d(acc, sc->red);
+  }
+  u64 k0 = cand < 2 ? 2 : cand;                              // :75  min(max(2, cand), topk)
+  if (k0 > (u64)P.topk) k0 = (u64)P.topk;
+  float span_key = key_of_pack(bound);
+  if (!(cand >= 2 && cand <= (u64)P.topk)) {
+    // rank form: the k0-th element of the order bounds the kept set.  Count histogram over
+    // all finite keys, then the same locate/collect/resolve as for masses.
+    rm.rank_form = true;
+    const float lowest = key_of_pack(pmin);
+    const float span = m - lowest;
+    const float scale = span > 0.0f ? (float)NB / span : 0.0f;
+    for (int i = tid; i < V; i += NT) {
+      const float k = keys[i];
+      if (k > -INFINITY) atomicAdd(&hist[bin_of(k, m, scale, NB)], (HistT)1);
+    }
+    __syncthreads();
+    sel_locate<HistT, NB>(hist, k0 - 1, sc);
+    const int tb = sc->sel_bin;
+    const u64 tprefix = sc->sel_prefix;
+    if (tb >= 0) {
+      for (int i = tid; i < V; i += NT) {
+        const float k = keys[i];
+        if (k > -INFINITY && bin_of(k, m, scale, NB) == tb) {
+          int slot = atomicAdd(&sc->list_count, 1);
+          if (slot < LIST_CAP) { list[slot].pack = pack_of(k, i); list[slot].w = 1; }
+        }
+      }
+    }
+    __syncthreads();
+    int n = sc->list_count;
+    if (n > LIST_CAP) { n = LIST_CAP; if (tid == 0 && P.status) atomicOr(&P.status[row], NS_ST_BIN_OVERFLOW); }
+    sel_resolve(list, n, k0 - 1, tprefix, sc);
+    // fewer finite keys than k0 (tiny vocabularies): keep them all
+    rm.bound_pack = sc->res_found ? pack_of(keys[sc->res_idx], sc->res_idx) : pmin;
+    __syncthreads();
+    for (int i = tid; i < NB; i += NT) hist[i] = 0;
+    if (tid == 0) sc->list_count = 0;
+    double acc = 0.0;
+    for (int i = tid; i < V; i += NT) {
+      const float k = keys[i];
+      if (pack_of(k, i) >= rm.bound_pack) acc += rm.e_of(k);
+    }
+    S = block_sum_d(acc, sc->red);
+    span_key = key_of_pack(rm.bound_pack);
+  } else {
+    rm.bound_pack = bound;
+  }
+  rm.C = __ddiv_rn((double)R, S);                            // :146  p/sum(p)*range
+
+  // ---- P3: bin widths, total mass, mass histogram; decode: mass before the observed token --
+  const float mspan = m - span_key;
+  const float mscale = mspan > 0.0f ? (float)NB / mspan : 0.0f;
+  int tok = -1;
+  u64 tok_pack = 0;
+  if (MODE == MODE_DEC) {
+    tok = P.token_in[(size_t)row * P.token_stride + slot];
+    if (tok < 0 || tok >= V) tok = top_id;
+    tok_pack = pack_of(keys[tok], tok);
+  }
+  u64 Q;
+  u64 mass_before_tok = 0;
+  {
+    u64 q_acc = 0, b_acc = 0;
+    for (int i = tid; i < V; i += NT) {
+      const float k = keys[i];
+      const u64 w = rm.mass(k, i);
+      if (MODE == MODE_DEBUG) dbg_q[(size_t)row * V + i] = w;
+      if (w != 0) {
+        atomicAdd(&hist[bin_of(k, m, mscale, NB)], (HistT)w);
+        q_acc += w;
+        if (MODE == MODE_DEC && pack_of(k, i) > tok_pack) b_acc += w;
+      }
+    }
+    Q = block_reduce_u(q_acc, OpAddU(), sc->red);
+    if (MODE == MODE_DEC) mass_before_tok = block_reduce_u(b_acc, OpAddU(), sc->red);
+  }
+  __syncthreads();
+
+  // selection helper (uniform control flow across the CTA)
+  auto select = [&](u64 tau, int* idx, u64* before, u64* w) -> bool {
+    sel_locate<HistT, NB>(hist, tau, sc);
+    const int tb = sc->sel_bin;
+    const u64 tprefix = sc->sel_prefix;
+    if (tid == 0) sc->list_count = 0;
+    __syncthreads();
+    if (tb < 0) return false;
+    for (int i = tid; i < V; i += NT) {
+      const float k = keys[i];
+      if (bin_of(k, m, mscale, NB) == tb) {
+        const u64 wi = rm.mass(k, i);
+        if (wi != 0) {
+          int slot = atomicAdd(&sc->list_count, 1);
+          if (slot < LIST_CAP) { list[slot].pack = pack_of(k, i); list[slot].w = wi; }
+        }
+      }
+    }
+    __syncthreads();
+    int n = sc->list_count;
+    if (n > LIST_CAP) { n = LIST_CAP; if (tid == 0 && P.status) atomicOr(&P.status[row], NS_ST_BIN_OVERFLOW); }
+    sel_resolve(list, n, tau, tprefix, sc);
+    const bool found = sc->res_found != 0;
+    *idx = sc->res_idx; *before = sc->res_before; *w = sc->res_w;
+    __syncthreads();
+    return found;
+  };
+
+  // ---- overfill: drop the tail of the order once the running total exceeds the range ------
+  u64 slack;
+  bool truncated = false;
+  u64 trunc_pack = 0;            // first dropped element
+  if (Q > R) {                                               // :153-155
+    int j; u64 bj, wj;
+    if (select(R, &j, &bj, &wj)) {
+      truncated = true;
+      trunc_pack = pack_of(keys[j], j);
+      slack = R - bj;                                        // :158
+    } else {
+      slack = 0;
+    }
+  } else {
+    slack = R - Q;                                           // :158
+  }
+
+  if (MODE == MODE_DEBUG) {
+    if (truncated) {
+      for (int i = tid; i < V; i += NT)
+        if (pack_of(keys[i], i) <= trunc_pack) dbg_q[(size_t)row * V + i] = 0;
+    }
+    if (tid == 0) {
+      dbg_meta[row * 4 + 0] = k0;
+      dbg_meta[row * 4 + 1] = slack;
+      dbg_meta[row * 4 + 2] = Q;
+      dbg_meta[row * 4 + 3] = R;
+    }
+    return;
+  }
+
+  const u64 top_mass = rm.mass(keys[top_id], top_id);
+  u64 nb, nt;
+  int token;
+  if (MODE == MODE_ENC) {
+    const int cursor = P.cursor[row];
+    const int mlen = P.msg_len[row];
+    const u64 window = ns_read_bits(P.msg + (size_t)row * P.msg_stride, cursor, mlen, P.precision);  // :168-171
+    const u64 m_rel = window - lo;
+    if (m_rel < top_mass + slack) {                          // rank 0 absorbs the slack (:158)
+      token = top_id; nb = lo; nt = lo + top_mass + slack;
+    } else {
+      int s; u64 bs, ws;
+      if (!select(m_rel - slack, &s, &bs, &ws)) { s = top_id; bs = 0; ws = top_mass; if (tid == 0 && P.status) atomicOr(&P.status[row], NS_ST_BIN_OVERFLOW); }
+      token = s;                                             // :172
+      if (s == top_id) { nb = lo; nt = lo + ws + slack; }
+      else { nb = lo + bs + slack; nt = nb + ws; }           // :175-176
+    }
+    if (tid == 0) {
+      uint64_t nlo, nhi;
+      const int n = ns_interval_update(nb, nt, P.precision, &nlo, &nhi);   // :179-190
+      P.lo[row] = nlo; P.hi[row] = nhi;
+      const int nc = cursor + n;                             // :184
+      P.cursor[row] = nc;
+      P.token_out[(size_t)row * P.token_stride + slot] = token;    // :202
+      if (P.ntok) P.ntok[row] = slot + 1;
+      if (P.nbits_out) P.nbits_out[row] = (uint8_t)n;
+      if (P.phase && nc >= mlen) P.phase[row] = P.finish_sent ? NS_PHASE_TAIL : NS_PHASE_DONE;   // :114
+      if (P.trace) { uint64_t* t = P.trace + (size_t)row * 4; t[0] = nb; t[1] = nt; t[2] = k0; t[3] = Q; }
+    }
+  } else {
+    // decode: rank of the observed token = mass in front of it (:298)
+    const u64 wt = rm.mass(keys[tok], tok);
+    bool in_range = (wt != 0 || rm.kept(keys[tok], tok, rm.e_of(keys[tok]))) && (!truncated || tok_pack > trunc_pack);
+    token = tok;
+    u64 bs = mass_before_tok, ws = wt;
+    if (!in_range) { token = top_id; bs = 0; ws = top_mass; }                 // :342 rank = 0
+    if (token == top_id) { nb = lo; nt = lo + ws + slack; }
+    else { nb = lo + bs + slack; nt = nb + ws; }                            // :347-348
+    if (tid == 0) {
+      uint64_t nlo, nhi;
+      const int n = ns_interval_update(nb, nt, P.precision, &nlo, &nhi);   // :351-366
+      P.lo[row] = nlo; P.hi[row] = nhi;
+      const bool last = P.ntok_total ? (slot == P.ntok_total[row] - 1) : (P.is_last && P.is_last[row]);
+      if (P.ntok) P.ntok[row] = slot + 1;
+      if (P.phase && P.ntok_total && slot + 1 >= P.ntok_total[row]) P.phase[row] = NS_PHASE_DONE;
+      const int olen = P.out_len[row];
+      uint32_t* ob = P.out_bits + (size_t)row * P.out_stride;
+      if (last) {                                            // :356-357 all precision bits of new_bottom
+        ns_write_bits(ob, olen, nb, P.precision);
+        P.out_len[row] = olen + P.precision;
+      } else {                                               // :359 first n bits of new_top-1
+        if (n > 0) ns_write_bits(ob, olen, (nt - 1) >> (P.precision - n), n);
+        P.out_len[row] = olen + n;
+      }
+      if (P.nbits_out) P.nbits_out[row] = (uint8_t)n;
+      if (!in_range && P.status) atomicOr(&P.status[row], NS_ST_OUT_OF_RANGE);
+      if (P.trace) { uint64_t* t = P.trace + (size_t)row * 4; t[0] = nb; t[1] = nt; t[2] = k0; t[3] = Q; }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------
+thread_local char g_err[256] = "";
+
+int set_err(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+
+int validate(const ns_ac_params* p, int mode) {
+  if (!p) return set_err(NS_E_NULL, "params is NULL");
+  if (!p->logits || !p->lo || !p->hi) return set_err(NS_E_NULL, "logits/lo/hi is NULL");
+  if (p->B < 0 || p->V < 4) return set_err(NS_E_RANGE, "B < 0 or V < 4");
+  if (p->V > MAX_VOCAB) return set_err(NS_E_VOCAB, "V exceeds the shared-memory row capacity (ns_ac_max_vocab)");
+  if (p->ld < p->V) return set_err(NS_E_RANGE, "ld < V");
+  if (p->precision < 2 || p->precision > 48) return set_err(NS_E_RANGE, "precision must be in [2, 48]");
+  if (p->topk < 1) return set_err(NS_E_RANGE, "topk must be >= 1");
+  if (!(p->temp > 0.0)) return set_err(NS_E_RANGE, "temp must be > 0");
+  if (((uintptr_t)p->logits & 3u) != 0) return set_err(NS_E_ALIGN, "logits not 4-byte aligned");
+  if (mode == MODE_ENC) {
+    if (!p->msg || !p->msg_len || !p->cursor || !p->token_out) return set_err(NS_E_NULL, "encode needs msg/msg_len/cursor/token_out");
+  } else if (mode == MODE_DEC) {
+    if (!p->token_in || !p->out_bits || !p->out_len) return set_err(NS_E_NULL, "decode needs token_in/out_bits/out_len");
+  }
+  return NS_OK;
+}
+
+template <int MODE, typename HistT>
+int launch(const ns_ac_params* p, u64* dbg_q, u64* dbg_meta, cudaStream_t st) {
+  const int smem = FIXED_BYTES + (p->V + 8) * 4;
+  static bool configured = false;   // per instantiation
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(ac_step_kernel<MODE, HistT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e != cudaSuccess) { set_err((int)e, cudaGetErrorString(e)); return e == cudaErrorInvalidDeviceFunction ? NS_E_NODEVICE : (int)e; }
+    configured = true;
+  }
+  if (p->B == 0) return NS_OK;
+  ac_step_kernel<MODE, HistT><<<p->B, NT, smem, st>>>(*p, dbg_q, dbg_meta);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_err((int)e, cudaGetErrorString(e));
+  return NS_OK;
+}
+
+template <int MODE>
+int dispatch(const ns_ac_params* p, u64* dbg_q, u64* dbg_meta, void* stream) {
+  int rc = validate(p, MODE);
+  if (rc != NS_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (p->precision <= 31) return launch<MODE, uint32_t>(p, dbg_q, dbg_meta, st);
+  return launch<MODE, u64>(p, dbg_q, dbg_meta, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ns_version(void) { return NS_ABI_VERSION; }
+const char* ns_last_error_string(void) { return g_err; }
+int ns_ac_max_vocab(void) { return MAX_VOCAB; }
+
+int ns_ac_encode_step(const ns_ac_params* p, void* cuda_stream) { return dispatch<MODE_ENC>(p, nullptr, nullptr, cuda_stream); }
+int ns_ac_decode_step(const ns_ac_params* p, void* cuda_stream) { return dispatch<MODE_DEC>(p, nullptr, nullptr, cuda_stream); }
+int ns_ac_debug_bins(const ns_ac_params* p, uint64_t* q_out, uint64_t* meta_out, void* cuda_stream) {
+  if (!q_out || !meta_out) return set_err(NS_E_NULL, "q_out/meta_out is NULL");
+  return dispatch<MODE_DEBUG>(p, (u64*)q_out, (u64*)meta_out, cuda_stream);
+}
+
+}  // extern "C"
