@@ -101,6 +101,8 @@ typedef struct ns_ac_params {
 
 int ns_version(void);
 const char* ns_last_error_string(void);
+/* sizeof(ns_ac_params) as compiled, so a binding can verify its struct mirror */
+int ns_sizeof_ac_params(void);
 /* largest V the arithmetic-coder kernels accept on this build */
 int ns_ac_max_vocab(void);
 

@@ -583,6 +583,7 @@ extern "C" {
 int ns_version(void) { return NS_ABI_VERSION; }
 const char* ns_last_error_string(void) { return g_err; }
 int ns_ac_max_vocab(void) { return MAX_VOCAB; }
+int ns_sizeof_ac_params(void) { return (int)sizeof(ns_ac_params); }
 
 int ns_ac_encode_step(const ns_ac_params* p, void* cuda_stream) { return dispatch<MODE_ENC>(p, nullptr, nullptr, cuda_stream); }
 int ns_ac_decode_step(const ns_ac_params* p, void* cuda_stream) { return dispatch<MODE_DEC>(p, nullptr, nullptr, cuda_stream); }

@@ -1,0 +1,186 @@
+"""Parity of the CUDA arithmetic coder (through the C ABI) with the oracle and the reference goldens."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ac_oracle as O
+from oracle.inputs import logits_pool, make_distinct, message_bits, rows_for
+
+pytestmark = pytest.mark.gpu
+
+
+def _streams(*a, **k):
+    from neuralsteganography_b200.coder import ArithmeticStreams
+    return ArithmeticStreams(*a, **k)
+
+
+def _run_encode_traced(st, fn, max_steps=400):
+    """Step with a host sync per token so the per-step trace can be compared (tests only)."""
+    trace = [[] for _ in range(st.B)]
+    for t in range(max_steps):
+        phase_before = st.phase.cpu().numpy().copy()
+        st.encode_step(fn(t))
+        torch.cuda.synchronize()
+        tr = st.trace.cpu().numpy()
+        nb = st.nbits.cpu().numpy()
+        lo = st.lo.cpu().numpy(); hi = st.hi.cpu().numpy()
+        for r in range(st.B):
+            if phase_before[r] == 0:
+                trace[r].append([int(tr[r, 0]), int(tr[r, 1]), int(nb[r]), int(lo[r]), int(hi[r])])
+        if st.all_done():
+            break
+    return trace
+
+
+def test_golden_cases_bit_exact(golden_dir, cases):
+    from gpu_util import PoolLogits, load_case
+    for cfg in cases["ac"]:
+        data, pool = load_case(golden_dir, cfg)
+        S = cfg["streams"]
+        fn = PoolLogits(pool, S)
+        st = _streams(S, cfg["V"], precision=cfg["precision"], temp=cfg["temp"], topk=cfg["topk"],
+                      token_cap=128, trace=True)
+        st.set_messages([data["msg_%d" % s].tolist() for s in range(S)])
+        trace = _run_encode_traced(st, fn)
+        toks = st.token_lists()
+        assert int(st.status.abs().sum().item()) == 0, cfg["name"]
+        for s in range(S):
+            assert toks[s] == data["tokens_%d" % s].tolist(), (cfg["name"], s, "tokens")
+            want = data["trace_%d" % s][:, :5]                 # new_bottom, new_top, nbits, lo, hi
+            assert np.array_equal(np.asarray(trace[s]), want), (cfg["name"], s, "interval trace")
+        # decode the reference's tokens
+        st.set_tokens([data["tokens_%d" % s].tolist() for s in range(S)])
+        bits = st.decode(fn)
+        assert int(st.status.abs().sum().item()) == 0
+        for s in range(S):
+            assert bits[s] == data["decoded_%d" % s].tolist(), (cfg["name"], s, "decoded bits")
+            msg = data["msg_%d" % s].tolist()
+            assert bits[s][: len(msg)] == msg
+
+
+@pytest.mark.parametrize("precision,topk,temp", [(26, 50257, 1.0), (26, 300, 0.9), (16, 50000, 1.0)])
+def test_integer_cdf_matches_oracle(precision, topk, temp):
+    """Bin widths of every token (the integer CDF of code_base/arithmetic.py:146-158), mid-stream ranges."""
+    V, B = 50257, 8
+    pool = logits_pool(77, B, V, 3.0)
+    st = _streams(B, V, precision=precision, temp=temp, topk=topk)
+    rng = np.random.default_rng(3)
+    los, his = [], []
+    for r in range(B):
+        width = int(rng.integers(2, 1 << precision)) if r else (1 << precision)
+        lo = int(rng.integers(0, (1 << precision) - width + 1))
+        los.append(lo); his.append(lo + width)
+    st.lo.copy_(torch.tensor(los)); st.hi.copy_(torch.tensor(his))
+    q, meta = st.debug_bins(torch.from_numpy(pool).cuda())
+    q = q.cpu().numpy(); meta = meta.cpu().numpy()
+    for r in range(B):
+        masked = O.mask_row(pool[r], O.ENC_MASK)
+        s, order = O.sort_desc(masked)
+        cum, k = O.integer_cdf(O.softmax_f64(s, temp), his[r] - los[r], topk)
+        widths = np.diff(np.concatenate([[0], cum]))
+        got = q[r][order[:k]].copy()
+        got[0] += meta[r, 1]                                   # slack goes to rank 0 (:158)
+        assert np.array_equal(got, widths), (r, "bin widths")
+        assert q[r][order[k:]].sum() == 0
+        assert meta[r, 3] == his[r] - los[r]
+
+
+def test_roundtrip_full_vocab_many_streams():
+    """4096-stream shape property: encode -> decode recovers every message exactly (config 3 sizes, fewer steps)."""
+    V, B, nbits, P = 50257, 512, 96, 3
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(1234)
+    pool = [torch.randn(B, V, generator=g, device=dev) * 3.0 for _ in range(P)]
+    fn = lambda t: pool[t % P]
+    msgs = [message_bits(4321 + r, nbits - (r % 5)).tolist() for r in range(B)]
+    st = _streams(B, V, precision=26, temp=1.0, topk=V, token_cap=64)
+    st.set_messages(msgs)
+    toks = st.encode(fn, poll_every=4)
+    assert st.all_done()
+    assert int((st.status & 2).sum().item()) == 0
+    st2 = _streams(B, V, precision=26, temp=1.0, topk=V, token_cap=64)
+    st2.set_tokens(toks)
+    bits = st2.decode(fn)
+    for r in range(B):
+        assert bits[r][: len(msgs[r])] == msgs[r], r
+    # a subset against the oracle on the same logits
+    for r in (0, 17, 255, 511):
+        rows = lambda t, r=r: pool[t % P][r].cpu().numpy()
+        res = O.encode_stream(rows, msgs[r], temp=1.0, precision=26, topk=V)
+        assert res.tokens == toks[r], r
+
+
+def test_ragged_empty_and_single_bit_messages():
+    V, B = 2048, 5
+    pool = logits_pool(11, 16, V, 3.0)
+    from gpu_util import PoolLogits
+    fn = PoolLogits(pool, B)
+    msgs = [[], [1], [0, 1, 1], message_bits(1, 40).tolist(), message_bits(2, 200).tolist()]
+    st = _streams(B, V, precision=16, temp=1.0, topk=50000, token_cap=128)
+    st.set_messages(msgs)
+    toks = st.encode(fn, poll_every=1)
+    assert toks[0] == []
+    for r in range(B):
+        res = O.encode_stream(rows_for(pool, r), msgs[r], temp=1.0, precision=16, topk=50000)
+        assert toks[r] == res.tokens, r
+    st.set_tokens(toks)
+    bits = st.decode(fn)
+    for r in range(B):
+        want, _ = O.decode_stream(rows_for(pool, r), toks[r], temp=1.0, precision=16, topk=50000)
+        assert bits[r] == want, r
+
+
+def test_ties_follow_lower_id_first():
+    """Rows with many exactly equal logits: order is (value desc, id asc) like the oracle."""
+    V, B = 4096, 4
+    rng = np.random.default_rng(5)
+    pool = np.round(rng.standard_normal((8, V)).astype(np.float32) * 4) / 2      # heavy duplication
+    from gpu_util import PoolLogits
+    fn = PoolLogits(pool, B)
+    msgs = [message_bits(50 + r, 120).tolist() for r in range(B)]
+    st = _streams(B, V, precision=20, temp=1.0, topk=50000, token_cap=128)
+    st.set_messages(msgs)
+    toks = st.encode(fn, poll_every=2)
+    flagged = (st.status.cpu().numpy() & 2) != 0
+    for r in range(B):
+        if flagged[r]:
+            continue                                            # bucket overflow is reported, not silent
+        res = O.encode_stream(rows_for(pool, r), msgs[r], temp=1.0, precision=20, topk=50000)
+        assert toks[r] == res.tokens, r
+
+
+def test_finish_sent_tail_and_out_of_range_token():
+    V, B = 2048, 2
+    pool = logits_pool(21, 8, V, 3.0)
+    from gpu_util import PoolLogits
+    fn = PoolLogits(pool, B)
+    sent_end = torch.zeros(V, dtype=torch.uint8, device="cuda")
+    top_per_step = [int(np.argmax(O.mask_row(rows_for(pool, 0)(t), O.ENC_MASK))) for t in range(40)]
+    msgs = [message_bits(9, 24).tolist(), message_bits(10, 24).tolist()]
+    st = _streams(B, V, precision=16, temp=1.0, topk=50000, token_cap=64, finish_sent=True, sent_end=sent_end)
+    st.set_messages(msgs)
+    base = O.encode_stream(rows_for(pool, 0), msgs[0], temp=1.0, precision=16, topk=50000).tokens
+    stop_at = len(base) + 2
+    sent_end[top_per_step[stop_at]] = 1                         # third tail token ends the sentence
+    toks = st.encode(fn, poll_every=1, max_steps=40)
+    assert toks[0][: len(base)] == base
+    tail = toks[0][len(base):]
+    assert tail == top_per_step[len(base): len(base) + len(tail)]      # rank-0 tokens (arithmetic.py:135-137)
+    assert tail[-1] == top_per_step[stop_at] or len(toks[0]) == 40
+    # decode with a token the kept set cannot contain (masked id V-1): flagged, coded as rank 0 (:342)
+    bad = [list(toks[0][: len(base)]), list(toks[1])]
+    bad[0][1] = V - 1
+    st.finish_sent = False
+    st.set_tokens(bad)
+    st.decode(fn)
+    assert int(st.status[0].item()) & 1
+
+
+def test_rejects_cpu_tensors_and_bad_shapes():
+    from neuralsteganography_b200 import NativeLibraryError
+    st = _streams(2, 2048, precision=16)
+    st.set_messages([[1, 0], [0, 1]])
+    with pytest.raises(NativeLibraryError):
+        st.encode_step(torch.zeros(2, 2048))
+    with pytest.raises(NativeLibraryError):
+        st.encode_step(torch.zeros(3, 2048, device="cuda"))
