@@ -45,8 +45,9 @@ extern "C" {
                                  code_base/arithmetic.py:301) -- coded as rank 0 like :342 */
 #define NS_ST_BIN_OVERFLOW 2  /* selection bucket exceeded the resolve capacity (degenerate
                                  logits, e.g. thousands of exactly equal values)       */
-#define NS_ST_EST_RETRY 4     /* provisional normaliser was outside its guard band; the row
-                                 was recomputed with the exact one (informational)     */
+#define NS_ST_EST_RETRY 4     /* informational: the throughput kernel handed this row to the exact
+                                 multi-pass kernel (top-k inside the cutoff set, estimate outside
+                                 its guard band, list overflow); results are identical */
 #define NS_ST_TOKEN_OVERFLOW 8 /* encode: token buffer full (ntok >= token_cap); stream stopped */
 
 /* Arithmetic coder (A): code_base/arithmetic.py:78-217 (encode), :220-373 (decode). */
@@ -95,8 +96,14 @@ typedef struct ns_ac_params {
   int32_t* out_len;     /* bits written so far per stream */
   /* ---- both ----------------------------------------------------------- */
   uint8_t* nbits_out;   /* bits consumed/emitted this step (arithmetic.py:183); may be NULL */
-  /* optional per-step trace for parity tests: [B,4] = new_bottom, new_top, k, selection-mass */
+  /* optional per-step trace for parity tests: [B,4] = new_bottom, new_top, k, total mass */
   uint64_t* trace;
+  /* Work queue, B+2 int32 zeroed once by the caller.  When given (and precision <= 31) a step is
+     two launches: the single-pass throughput kernel, then the exact multi-pass kernel on the rows
+     the first one queued here (top-k inside the cutoff set, degenerate rows).  NULL = exact kernel
+     only.  force_exact != 0 also selects the exact kernel only. */
+  int32_t* slow_ws;
+  int32_t force_exact;
 } ns_ac_params;
 
 int ns_version(void);

@@ -61,7 +61,7 @@ class ArithmeticStreams:
     def __init__(self, batch: int, vocab: int, *, precision: int = 16, temp: float = 1.0,
                  topk: int = 50000, finish_sent: bool = False, device="cuda",
                  mask_ids: Optional[Sequence[int]] = None, token_cap: int = 1024,
-                 sent_end: Optional[torch.Tensor] = None, trace: bool = False):
+                 sent_end: Optional[torch.Tensor] = None, trace: bool = False, force_exact: bool = False):
         self.lib = N.load()
         if not torch.cuda.is_available():
             raise N.NativeLibraryError("no CUDA device: the coder has no CPU fallback")
@@ -86,6 +86,8 @@ class ArithmeticStreams:
         self.tokens = torch.full((self.B, self.token_cap), -1, dtype=torch.int32, device=d)
         self.trace = torch.zeros((self.B, 4), dtype=torch.int64, device=d) if trace else None
         self.sent_end = sent_end
+        self.force_exact = bool(force_exact)
+        self.slow_ws = torch.zeros(self.B + 2, dtype=torch.int32, device=d)
         self.msg = None
         self.msg_len = None
         self.ntok_total = None
@@ -156,6 +158,8 @@ class ArithmeticStreams:
         p.ntok_total = N.ptr(self.ntok_total)
         p.nbits_out = self.nbits.data_ptr()
         p.trace = N.ptr(self.trace)
+        p.slow_ws = self.slow_ws.data_ptr()
+        p.force_exact = int(self.force_exact)
         return p
 
     def encode_step(self, logits: torch.Tensor) -> None:

@@ -199,17 +199,65 @@ __device__ void sel_resolve(const ListEntry* list, int n, u64 tau, u64 prefix, S
 
 enum { MODE_ENC = 0, MODE_DEC = 1, MODE_DEBUG = 2 };
 
+// ---- per-stream epilogues (one thread) ---------------------------------------------------------
+// encode: consume the shared prefix, rescale, emit the token (code_base/arithmetic.py:179-203)
+__device__ __forceinline__ void finish_encode(const ns_ac_params& P, int row, int slot, int token,
+                                              u64 nb, u64 nt, u64 k0, u64 Q) {
+  const int cursor = P.cursor[row];
+  const int mlen = P.msg_len[row];
+  uint64_t nlo, nhi;
+  const int n = ns_interval_update(nb, nt, P.precision, &nlo, &nhi);   // :179-190
+  P.lo[row] = nlo; P.hi[row] = nhi;
+  const int nc = cursor + n;                                 // :184
+  P.cursor[row] = nc;
+  P.token_out[(size_t)row * P.token_stride + slot] = token;  // :202
+  if (P.ntok) P.ntok[row] = slot + 1;
+  if (P.nbits_out) P.nbits_out[row] = (uint8_t)n;
+  if (P.phase && nc >= mlen) P.phase[row] = P.finish_sent ? NS_PHASE_TAIL : NS_PHASE_DONE;   // :114
+  if (P.trace) { uint64_t* t = P.trace + (size_t)row * 4; t[0] = nb; t[1] = nt; t[2] = k0; t[3] = Q; }
+}
+
+// finish_sent tail: rank-0 token, interval untouched (arithmetic.py:135-137)
+__device__ __forceinline__ void finish_tail(const ns_ac_params& P, int row, int slot, int top_id) {
+  P.token_out[(size_t)row * P.token_stride + slot] = top_id;
+  if (P.ntok) P.ntok[row] = slot + 1;
+  if (P.nbits_out) P.nbits_out[row] = 0;
+  if (P.phase && P.sent_end && P.sent_end[top_id]) P.phase[row] = NS_PHASE_DONE;
+}
+
+// decode: emit the shared prefix (all `precision` bits of new_bottom on the last token), rescale
+// (code_base/arithmetic.py:351-366)
+__device__ __forceinline__ void finish_decode(const ns_ac_params& P, int row, int slot, bool in_range,
+                                              u64 nb, u64 nt, u64 k0, u64 Q) {
+  uint64_t nlo, nhi;
+  const int n = ns_interval_update(nb, nt, P.precision, &nlo, &nhi);
+  P.lo[row] = nlo; P.hi[row] = nhi;
+  const bool last = P.ntok_total ? (slot == P.ntok_total[row] - 1) : (P.is_last && P.is_last[row]);
+  if (P.ntok) P.ntok[row] = slot + 1;
+  if (P.phase && P.ntok_total && slot + 1 >= P.ntok_total[row]) P.phase[row] = NS_PHASE_DONE;
+  const int olen = P.out_len[row];
+  uint32_t* ob = P.out_bits + (size_t)row * P.out_stride;
+  if (last) {                                                // :356-357
+    ns_write_bits(ob, olen, nb, P.precision);
+    P.out_len[row] = olen + P.precision;
+  } else {                                                   // :359
+    if (n > 0) ns_write_bits(ob, olen, (nt - 1) >> (P.precision - n), n);
+    P.out_len[row] = olen + n;
+  }
+  if (P.nbits_out) P.nbits_out[row] = (uint8_t)n;
+  if (!in_range && P.status) atomicOr(&P.status[row], NS_ST_OUT_OF_RANGE);
+  if (P.trace) { uint64_t* t = P.trace + (size_t)row * 4; t[0] = nb; t[1] = nt; t[2] = k0; t[3] = Q; }
+}
+
 template <int MODE, typename HistT>
-__global__ void __launch_bounds__(NT, 1) ac_step_kernel(ns_ac_params P, u64* dbg_q, u64* dbg_meta) {
+__device__ void ac_exact_row(const ns_ac_params& P, const int row, u64* dbg_q, u64* dbg_meta, unsigned char* smem_raw) {
   constexpr int NB = HIST_BYTES / (int)sizeof(HistT);
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   double* tab = reinterpret_cast<double*>(smem_raw);
   HistT* hist = reinterpret_cast<HistT*>(smem_raw + NS_EXP_N * 8);
   ListEntry* list = reinterpret_cast<ListEntry*>(smem_raw + NS_EXP_N * 8 + HIST_BYTES);
   Scalars* sc = reinterpret_cast<Scalars*>(smem_raw + NS_EXP_N * 8 + HIST_BYTES + LIST_CAP * sizeof(ListEntry));
   float* keys_base = reinterpret_cast<float*>(smem_raw + FIXED_BYTES);
 
-  const int row = blockIdx.x;
   const int tid = threadIdx.x;
   const int V = P.V;
   uint8_t phase = P.phase ? P.phase[row] : (uint8_t)NS_PHASE_CODING;
@@ -273,12 +321,7 @@ __global__ void __launch_bounds__(NT, 1) ac_step_kernel(ns_ac_params P, u64* dbg
 
   if (MODE == MODE_ENC && phase == NS_PHASE_TAIL) {
     // finish_sent tail: rank-0 token, interval untouched (arithmetic.py:135-137)
-    if (tid == 0) {
-      P.token_out[(size_t)row * P.token_stride + slot] = top_id;
-      if (P.ntok) P.ntok[row] = slot + 1;
-      if (P.nbits_out) P.nbits_out[row] = 0;
-      if (P.phase && P.sent_end && P.sent_end[top_id]) P.phase[row] = NS_PHASE_DONE;
-    }
+    if (tid == 0) finish_tail(P, row, slot, top_id);
     return;
   }
 
@@ -479,18 +522,7 @@ __global__ void __launch_bounds__(NT, 1) ac_step_kernel(ns_ac_params P, u64* dbg
       if (s == top_id) { nb = lo; nt = lo + ws + slack; }
       else { nb = lo + bs + slack; nt = nb + ws; }           // :175-176
     }
-    if (tid == 0) {
-      uint64_t nlo, nhi;
-      const int n = ns_interval_update(nb, nt, P.precision, &nlo, &nhi);   // :179-190
-      P.lo[row] = nlo; P.hi[row] = nhi;
-      const int nc = cursor + n;                             // :184
-      P.cursor[row] = nc;
-      P.token_out[(size_t)row * P.token_stride + slot] = token;    // :202
-      if (P.ntok) P.ntok[row] = slot + 1;
-      if (P.nbits_out) P.nbits_out[row] = (uint8_t)n;
-      if (P.phase && nc >= mlen) P.phase[row] = P.finish_sent ? NS_PHASE_TAIL : NS_PHASE_DONE;   // :114
-      if (P.trace) { uint64_t* t = P.trace + (size_t)row * 4; t[0] = nb; t[1] = nt; t[2] = k0; t[3] = Q; }
-    }
+    if (tid == 0) finish_encode(P, row, slot, token, nb, nt, k0, Q);
   } else {
     // decode: rank of the observed token = mass in front of it (:298)
     const u64 wt = rm.mass(keys[tok], tok);
@@ -500,28 +532,33 @@ __global__ void __launch_bounds__(NT, 1) ac_step_kernel(ns_ac_params P, u64* dbg
     if (!in_range) { token = top_id; bs = 0; ws = top_mass; }                 // :342 rank = 0
     if (token == top_id) { nb = lo; nt = lo + ws + slack; }
     else { nb = lo + bs + slack; nt = nb + ws; }                            // :347-348
-    if (tid == 0) {
-      uint64_t nlo, nhi;
-      const int n = ns_interval_update(nb, nt, P.precision, &nlo, &nhi);   // :351-366
-      P.lo[row] = nlo; P.hi[row] = nhi;
-      const bool last = P.ntok_total ? (slot == P.ntok_total[row] - 1) : (P.is_last && P.is_last[row]);
-      if (P.ntok) P.ntok[row] = slot + 1;
-      if (P.phase && P.ntok_total && slot + 1 >= P.ntok_total[row]) P.phase[row] = NS_PHASE_DONE;
-      const int olen = P.out_len[row];
-      uint32_t* ob = P.out_bits + (size_t)row * P.out_stride;
-      if (last) {                                            // :356-357 all precision bits of new_bottom
-        ns_write_bits(ob, olen, nb, P.precision);
-        P.out_len[row] = olen + P.precision;
-      } else {                                               // :359 first n bits of new_top-1
-        if (n > 0) ns_write_bits(ob, olen, (nt - 1) >> (P.precision - n), n);
-        P.out_len[row] = olen + n;
-      }
-      if (P.nbits_out) P.nbits_out[row] = (uint8_t)n;
-      if (!in_range && P.status) atomicOr(&P.status[row], NS_ST_OUT_OF_RANGE);
-      if (P.trace) { uint64_t* t = P.trace + (size_t)row * 4; t[0] = nb; t[1] = nt; t[2] = k0; t[3] = Q; }
-    }
+    if (tid == 0) finish_decode(P, row, slot, in_range, nb, nt, k0, Q);
   }
 }
+
+// One CTA per row (slow_ws == nullptr), or a small persistent grid draining the rows the fast
+// kernel queued in slow_ws = {count, done, rows...}; the last CTA to finish resets the queue.
+template <int MODE, typename HistT>
+__global__ void __launch_bounds__(NT, 1) ac_step_kernel(ns_ac_params P, u64* dbg_q, u64* dbg_meta, int32_t* slow_ws) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (!slow_ws) {
+    ac_exact_row<MODE, HistT>(P, blockIdx.x, dbg_q, dbg_meta, smem_raw);
+    return;
+  }
+  const int count = slow_ws[0];
+  for (int it = blockIdx.x; it < count; it += gridDim.x) {
+    __syncthreads();
+    ac_exact_row<MODE, HistT>(P, slow_ws[2 + it], dbg_q, dbg_meta, smem_raw);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int d = atomicAdd(&slow_ws[1], 1);
+    if (d == (int)gridDim.x - 1) { slow_ws[0] = 0; slow_ws[1] = 0; __threadfence(); }
+  }
+}
+
+#include "ns_fast.cuh"
 
 // ------------------------------------------------------------------------------------
 // host side
@@ -551,20 +588,59 @@ int validate(const ns_ac_params* p, int mode) {
   return NS_OK;
 }
 
-template <int MODE, typename HistT>
-int launch(const ns_ac_params* p, u64* dbg_q, u64* dbg_meta, cudaStream_t st) {
-  const int smem = FIXED_BYTES + (p->V + 8) * 4;
-  static bool configured = false;   // per instantiation
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(ac_step_kernel<MODE, HistT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-    if (e != cudaSuccess) { set_err((int)e, cudaGetErrorString(e)); return e == cudaErrorInvalidDeviceFunction ? NS_E_NODEVICE : (int)e; }
-    configured = true;
+int g_num_sms = 0;
+
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      g_num_sms = n;
+    else
+      g_num_sms = 148;
   }
-  if (p->B == 0) return NS_OK;
-  ac_step_kernel<MODE, HistT><<<p->B, NT, smem, st>>>(*p, dbg_q, dbg_meta);
+  return g_num_sms;
+}
+
+template <typename K>
+int configure(K kernel, bool* done) {
+  if (*done) return NS_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  if (e != cudaSuccess) { set_err((int)e, cudaGetErrorString(e)); return e == cudaErrorInvalidDeviceFunction ? NS_E_NODEVICE : (int)e; }
+  *done = true;
+  return NS_OK;
+}
+
+int check_launch() {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_err((int)e, cudaGetErrorString(e));
   return NS_OK;
+}
+
+// exact kernel: one CTA per row, or (slow_ws given) a 32-CTA grid draining the hand-over queue
+template <int MODE, typename HistT>
+int launch_exact(const ns_ac_params* p, u64* dbg_q, u64* dbg_meta, int32_t* slow_ws, cudaStream_t st) {
+  const int smem = FIXED_BYTES + (p->V + 8) * 4;
+  static bool configured = false;
+  int rc = configure(ac_step_kernel<MODE, HistT>, &configured);
+  if (rc != NS_OK) return rc;
+  if (p->B == 0) return NS_OK;
+  const int grid = slow_ws ? (p->B < 32 ? p->B : 32) : p->B;
+  ac_step_kernel<MODE, HistT><<<grid, NT, smem, st>>>(*p, dbg_q, dbg_meta, slow_ws);
+  return check_launch();
+}
+
+// fast kernel: persistent, one CTA per SM
+template <bool UNIT, int MODE>
+int launch_fast(const ns_ac_params* p, cudaStream_t st) {
+  const int smem = FIXED_BYTES + (p->V + 8) * 4;
+  static bool configured = false;
+  int rc = configure(ac_fast_kernel<UNIT, MODE>, &configured);
+  if (rc != NS_OK) return rc;
+  if (p->B == 0) return NS_OK;
+  const int sms = num_sms();
+  const int grid = p->B < sms ? p->B : sms;
+  ac_fast_kernel<UNIT, MODE><<<grid, FT, smem, st>>>(*p, p->slow_ws);
+  return check_launch();
 }
 
 template <int MODE>
@@ -572,8 +648,14 @@ int dispatch(const ns_ac_params* p, u64* dbg_q, u64* dbg_meta, void* stream) {
   int rc = validate(p, MODE);
   if (rc != NS_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (p->precision <= 31) return launch<MODE, uint32_t>(p, dbg_q, dbg_meta, st);
-  return launch<MODE, u64>(p, dbg_q, dbg_meta, st);
+  if (p->precision > 31) return launch_exact<MODE, u64>(p, dbg_q, dbg_meta, nullptr, st);
+  if (MODE == MODE_DEBUG || p->slow_ws == nullptr || p->force_exact)
+    return launch_exact<MODE, uint32_t>(p, dbg_q, dbg_meta, nullptr, st);
+  // throughput path: fast kernel, then the exact kernel on whatever it handed over
+  rc = (p->temp == 1.0) ? launch_fast<true, MODE == MODE_DEBUG ? MODE_ENC : MODE>(p, st)
+                        : launch_fast<false, MODE == MODE_DEBUG ? MODE_ENC : MODE>(p, st);
+  if (rc != NS_OK) return rc;
+  return launch_exact<MODE, uint32_t>(p, dbg_q, dbg_meta, p->slow_ws, st);
 }
 
 }  // namespace
