@@ -649,7 +649,7 @@ int dispatch(const ns_ac_params* p, u64* dbg_q, u64* dbg_meta, void* stream) {
   if (rc != NS_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (p->precision > 31) return launch_exact<MODE, u64>(p, dbg_q, dbg_meta, nullptr, st);
-  if (MODE == MODE_DEBUG || p->slow_ws == nullptr || p->force_exact)
+  if (MODE == MODE_DEBUG || p->slow_ws == nullptr || p->force_exact || p->V < F_MIN_VOCAB)
     return launch_exact<MODE, uint32_t>(p, dbg_q, dbg_meta, nullptr, st);
   // throughput path: fast kernel, then the exact kernel on whatever it handed over
   rc = (p->temp == 1.0) ? launch_fast<true, MODE == MODE_DEBUG ? MODE_ENC : MODE>(p, st)

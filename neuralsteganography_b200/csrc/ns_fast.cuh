@@ -1,9 +1,10 @@
 // ns_fast.cuh -- single-exp-pass arithmetic-coder step (the throughput path), sm_100a.
-// Included by ns_coder.cu after the shared definitions (u64, pack_of, ListEntry, finish_*).
+// Included by ns_coder.cu after the shared definitions (u64, pack_of, finish_*).
 //
 // Persistent CTAs (one per SM, 512 threads), each looping over rows.  Per row:
-//   L   128-bit global loads -> shared words[] ; fused fp32 online softmax estimate
-//       (row max, its lowest id, sum of exp) ; L2 prefetch of the CTA's next row
+//   L   the row is pulled into shared memory by the bulk-copy engine (cp.async.bulk, 8 pieces, one
+//       mbarrier each); while pieces land, an fp32 online softmax estimate (row max, its lowest id,
+//       sum of exp) runs over the pieces already there.  The CTA's next row is prefetched into L2.
 //   P1  ONE fp64 exp per element (10 fp64 ops): exact sum of all e_i in a fixed order, exact sum of
 //       the provisionally-cut ones, elements within 2^-10 of the provisional cutoff go to a small
 //       list with their exact e ; the word is overwritten in place by trunc_fp32(e_i) (0 if not kept)
@@ -11,8 +12,9 @@
 //       S_kept and C = range / S_kept exact
 //   P2  q_i = rint(e_i * C) from the truncated e_i with a rigorous interval test (2 fp64 FMAs);
 //       the few undecidable ones are redone exactly from the original logit (L2 hit) ;
-//       integer mass histogram over 2048 monotone buckets of the fp32 bit pattern ; total mass
-//   SEL/UPD as in the exact kernel (bucket prefix -> collect -> exact order by original logit).
+//       integer mass histogram over 2048 monotone buckets of the fp32 bit pattern
+//   SEL bucket prefix -> gather the target bucket -> exact order (e32, then original logit, then id)
+//   UPD shared-prefix bits + interval rescale (finish_encode / finish_decode)
 // Anything unusual (top-k smaller than the cutoff set, list overflow, estimate outside its guard
 // band) queues the row in slow_ws; the exact multi-pass kernel then redoes it.  The decision only
 // depends on the row and its range, never on encode/decode, so both directions take the same path.
@@ -20,23 +22,30 @@
 constexpr int FT = 512;              // threads per CTA
 constexpr int FW = FT / 32;
 constexpr int F_NB = 2048;           // histogram buckets (u32 masses: precision <= 31)
+constexpr int F_BPT = F_NB / FT;     // buckets per thread in the scan
 constexpr int F_BAND_CAP = 128;
 constexpr int F_U_CAP = 256;
 constexpr int F_C_CAP = 256;
+constexpr int F_PIECES = 8;          // bulk-copy pieces per row
+constexpr int F_MIN_VOCAB = 256;     // below this the exact kernel is used
 constexpr float F_BAND_EPS = 0.0009765625f;   // 2^-10 half-width (in log units) of the exact-list band
 constexpr uint32_t F_TOP = 0x3F800000u;       // bit pattern of 1.0f = e of the row maximum
 
+// hand-over reasons (status bits 8..15, diagnostics only)
+enum { F_WHY_EST = 1, F_WHY_BAND = 2, F_WHY_VERIFY = 3, F_WHY_RANK = 4, F_WHY_ULIST = 5 };
+
 struct BandEntry { int id; int kept; double e; };
+struct CandEntry { uint32_t ebits; int id; uint32_t w; float key; };   // 16 B
 
 struct FScal {
-  u64 red[FW];
-  float M; int top_id; float sum32; int remax;
+  u64 red[3 * FW];
+  u64 bar[F_PIECES];                 // mbarriers of the row copy
+  float sum32; int remax; float M; int top_id;
   int band_n; int u_n; int c_n; int bail;
   u64 band_cut_int;
   int sel_bin; u64 sel_prefix;
   int res_idx; u64 res_before; u64 res_w; int res_found;
-  // row constants (written by thread 0, read by everybody)
-  double dm, thr; float kappa_lo, kappa_hi, clamp_key; int band_E;
+  float kappa_lo, kappa_hi, clamp_key; int band_E;
 };
 static_assert(sizeof(FScal) <= 1024, "FScal too large");
 static_assert(NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16 + F_U_CAP * 4 + F_C_CAP * 16 + 1024 <= FIXED_BYTES, "fast smem layout");
@@ -46,21 +55,39 @@ __device__ __forceinline__ float f_ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float4 f_ldg4(const float4* p) {
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
-}
 __device__ __forceinline__ void f_prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
 }
+__device__ __forceinline__ uint32_t f_smem_addr(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void f_mbar_init(u64* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(f_smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void f_mbar_expect_tx(u64* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(f_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void f_bulk_g2s(void* dst, const void* src, uint32_t bytes, u64* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(f_smem_addr(dst)), "l"(src), "r"(bytes), "r"(f_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void f_mbar_wait(u64* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}\n" :: "r"(f_smem_addr(bar)), "r"(parity) : "memory");
+}
 
 // queue a row for the exact kernel: slow_ws = {count, done, rows...}
-__device__ __forceinline__ void hand_over(const ns_ac_params& P, int32_t* slow_ws, int row) {
+__device__ __forceinline__ void hand_over(const ns_ac_params& P, int32_t* slow_ws, int row, int why) {
   const int s = atomicAdd(&slow_ws[0], 1);
   slow_ws[2 + s] = row;
-  if (P.status) atomicOr(&P.status[row], NS_ST_EST_RETRY);   // informational: row took the exact path
+  if (P.status) atomicOr(&P.status[row], NS_ST_EST_RETRY | (why << 8));   // informational
 }
 
 template <class Op>
@@ -75,17 +102,6 @@ __device__ __forceinline__ u64 f_reduce_u(u64 v, Op op, u64* scratch) {
   for (int w = 1; w < FW; ++w) r = op(r, scratch[w]);
   return r;
 }
-__device__ __forceinline__ double f_sum_d(double v, u64* scratch) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = (u64)__double_as_longlong(v);
-  __syncthreads();
-  double r = __longlong_as_double((long long)scratch[0]);
-#pragma unroll
-  for (int w = 1; w < FW; ++w) r = r + __longlong_as_double((long long)scratch[w]);
-  return r;
-}
 __device__ __forceinline__ float f_sum_f(float v, u64* scratch) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, o);
@@ -97,13 +113,33 @@ __device__ __forceinline__ float f_sum_f(float v, u64* scratch) {
   for (int w = 1; w < FW; ++w) r = r + __uint_as_float((uint32_t)scratch[w]);
   return r;
 }
-
-// online softmax step of one lane-private accumulator: (tm, ts, ti) <- element (x, id)
-#define F_ONLINE(x, id, tm, ts, ti)                               \
-  do {                                                            \
-    if ((x) > (tm)) { (ts) *= f_ex2(((tm) - (x)) * c2); (tm) = (x); (ti) = (id); } \
-    (ts) += f_ex2(((x) - (tm)) * c2);                             \
-  } while (0)
+// two fp64 sums and one integer sum with a single pair of barriers; fixed order -> deterministic bits
+__device__ __forceinline__ void f_sum_ddu(double& a, double& b, u64& c, u64* scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a = a + __shfl_xor_sync(0xffffffffu, a, o);
+    b = b + __shfl_xor_sync(0xffffffffu, b, o);
+    c = c + __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+    const int w = threadIdx.x >> 5;
+    scratch[w] = (u64)__double_as_longlong(a);
+    scratch[FW + w] = (u64)__double_as_longlong(b);
+    scratch[2 * FW + w] = c;
+  }
+  __syncthreads();
+  double ra = __longlong_as_double((long long)scratch[0]);
+  double rb = __longlong_as_double((long long)scratch[FW]);
+  u64 rc = scratch[2 * FW];
+#pragma unroll
+  for (int w = 1; w < FW; ++w) {
+    ra = ra + __longlong_as_double((long long)scratch[w]);
+    rb = rb + __longlong_as_double((long long)scratch[FW + w]);
+    rc = rc + scratch[2 * FW + w];
+  }
+  a = ra; b = rb; c = rc;
+}
 
 template <bool UNIT_TEMP, int MODE>
 __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t* slow_ws) {
@@ -112,7 +148,7 @@ __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t*
   uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + NS_EXP_N * 8);
   BandEntry* band = reinterpret_cast<BandEntry*>(smem_raw + NS_EXP_N * 8 + F_NB * 4);
   int* ulist = reinterpret_cast<int*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16);
-  ListEntry* clist = reinterpret_cast<ListEntry*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16 + F_U_CAP * 4);
+  CandEntry* clist = reinterpret_cast<CandEntry*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16 + F_U_CAP * 4);
   FScal* sc = reinterpret_cast<FScal*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16 + F_U_CAP * 4 + F_C_CAP * 16);
   float* words = reinterpret_cast<float*>(smem_raw + FIXED_BYTES);   // element id lives at words[id + mis]
   float4* w4 = reinterpret_cast<float4*>(words);
@@ -124,6 +160,11 @@ __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t*
   const double magic = 6755399441055744.0;                 // 1.5 * 2^52
 
   for (int i = tid; i < NS_EXP_N; i += FT) tab[i] = c_exp_tab[i];
+  if (tid == 0) {
+    for (int k = 0; k < F_PIECES; ++k) f_mbar_init(&sc->bar[k], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t parity = 0;                                     // bit k: phase parity of piece k's mbarrier
 
   for (int row = blockIdx.x; row < P.B; row += gridDim.x) {
     __syncthreads();                                       // previous row is finished with shared memory
@@ -143,34 +184,35 @@ __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t*
       continue;
     }
 
-    // ------------------------------------------------------------------ L: load + estimate
+    // ------------------------------------------------------------------ L: bulk copy + estimate
     const float* g = P.logits + (size_t)row * (size_t)P.ld;
     const int mis = (int)(((uintptr_t)g & 15u) >> 2);
     const int W4 = (mis + V + 3) >> 2;                     // float4 chunks of the padded row
-    const float4* g4 = reinterpret_cast<const float4*>(g - mis);
-    for (int i = tid; i < F_NB / 4; i += FT) reinterpret_cast<uint4*>(hist)[i] = make_uint4(0, 0, 0, 0);
-    if (tid == 0) { sc->band_n = 0; sc->u_n = 0; sc->c_n = 0; sc->bail = 0; sc->band_cut_int = 0; sc->remax = 0; }
-    float tm0 = -3.0e38f, tm1 = -3.0e38f, tm2 = -3.0e38f, tm3 = -3.0e38f;
-    float ts0 = 0.f, ts1 = 0.f, ts2 = 0.f, ts3 = 0.f;
-    int ti0 = 0, ti1 = 0, ti2 = 0, ti3 = 0;
-    for (int c = tid; c < W4; c += FT) {
-      float4 v;
-      const int b = 4 * c - mis;
-      if (c > 0 && c < W4 - 1) {
-        v = f_ldg4(g4 + c);
-      } else {
-        v.x = (b >= 0 && b < V) ? g[b] : -INFINITY;
-        v.y = (b + 1 >= 0 && b + 1 < V) ? g[b + 1] : -INFINITY;
-        v.z = (b + 2 >= 0 && b + 2 < V) ? g[b + 2] : -INFINITY;
-        v.w = (b + 3 >= 0 && b + 3 < V) ? g[b + 3] : -INFINITY;
+    const int NI = W4 - 2;                                 // interior chunks: wholly inside the row
+    const int PC = (NI + F_PIECES - 1) / F_PIECES;         // chunks per piece
+    if (tid == 0) {
+      // generic-proxy accesses of the previous row are ordered before the async-proxy writes
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const char* src = reinterpret_cast<const char*>(g - mis) + 16;
+      char* dst = reinterpret_cast<char*>(w4 + 1);
+      for (int k = 0; k < F_PIECES; ++k) {
+        const int c0 = k * PC;
+        int n = NI - c0;
+        if (n > PC) n = PC;
+        if (n > 0) {
+          f_mbar_expect_tx(&sc->bar[k], (uint32_t)n * 16u);
+          f_bulk_g2s(dst + (size_t)c0 * 16, src + (size_t)c0 * 16, (uint32_t)n * 16u, &sc->bar[k]);
+        }
       }
-      v.x += 0.0f; v.y += 0.0f; v.z += 0.0f; v.w += 0.0f;  // -0 -> +0 (equal logits tie by id)
-      w4[c] = v;
-      F_ONLINE(v.x, b, tm0, ts0, ti0);
-      F_ONLINE(v.y, b + 1, tm1, ts1, ti1);
-      F_ONLINE(v.z, b + 2, tm2, ts2, ti2);
-      F_ONLINE(v.w, b + 3, tm3, ts3, ti3);
+      sc->band_n = 0; sc->u_n = 0; sc->c_n = 0; sc->bail = 0; sc->band_cut_int = 0; sc->remax = 0;
     }
+    // the two edge chunks may straddle the row ends: plain loads, -inf padding
+    if (tid < 8) {
+      const int c = tid < 4 ? 0 : W4 - 1;
+      const int b = 4 * c - mis + (tid & 3);
+      words[4 * c + (tid & 3)] = (b >= 0 && b < V) ? g[b] : -INFINITY;
+    }
+    for (int i = tid; i < F_NB / 4; i += FT) reinterpret_cast<uint4*>(hist)[i] = make_uint4(0, 0, 0, 0);
     {   // prefetch this CTA's next row into L2 while this one is processed
       const int nrow = row + gridDim.x;
       if (nrow < P.B) {
@@ -179,20 +221,32 @@ __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t*
         for (int off = tid * 128; off < nbytes; off += FT * 128) f_prefetch_l2(np + off);
       }
     }
-    float Mt = fmaxf(fmaxf(tm0, tm1), fmaxf(tm2, tm3));
-    u64 pk = 0;
-    {
-      u64 p0 = pack_of(tm0, ti0), p1 = pack_of(tm1, ti1), p2 = pack_of(tm2, ti2), p3 = pack_of(tm3, ti3);
-      pk = p0 > p1 ? p0 : p1;
-      u64 pq = p2 > p3 ? p2 : p3;
-      pk = pk > pq ? pk : pq;
+    // fp32 online softmax over the pieces as they land: (tm, ts) per thread, lowest id of the max
+    float tm = -3.0e38f, ts = 0.f;
+    int ti = 0;
+    auto online4 = [&](const float4 v, const int b) {
+      const float cm = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+      if (cm > tm) {
+        ts *= f_ex2((tm - cm) * c2);
+        tm = cm;
+        ti = (v.x == cm) ? b : (v.y == cm) ? b + 1 : (v.z == cm) ? b + 2 : b + 3;
+      }
+      ts += (f_ex2((v.x - tm) * c2) + f_ex2((v.y - tm) * c2)) + (f_ex2((v.z - tm) * c2) + f_ex2((v.w - tm) * c2));
+    };
+    for (int k = 0; k < F_PIECES; ++k) {
+      const int c0 = 1 + k * PC;
+      int c1 = c0 + PC;
+      if (c1 > 1 + NI) c1 = 1 + NI;
+      if (c0 < c1) { f_mbar_wait(&sc->bar[k], (parity >> k) & 1u); parity ^= (1u << k); }
+      for (int c = c0 + tid; c < c1; c += FT) online4(w4[c], 4 * c - mis);
     }
-    float tst = ts0 * f_ex2((tm0 - Mt) * c2) + ts1 * f_ex2((tm1 - Mt) * c2) + ts2 * f_ex2((tm2 - Mt) * c2) +
-                ts3 * f_ex2((tm3 - Mt) * c2);
-    const u64 pmax = f_reduce_u(pk, OpMaxU(), sc->red);
+    __syncthreads();                                       // edge chunks written by threads 0..7
+    if (tid == 0) online4(w4[0], -mis);
+    if (tid == 32) online4(w4[W4 - 1], 4 * (W4 - 1) - mis);
+    const u64 pmax = f_reduce_u(pack_of(tm + 0.0f, ti), OpMaxU(), sc->red);
     float M = key_of_pack(pmax);
     int top_id = id_of_pack(pmax);
-    float ssum = f_sum_f(tst * f_ex2((Mt - M) * c2), sc->red);
+    float ssum = f_sum_f(ts * f_ex2((tm - M) * c2), sc->red);
     // forbidden tokens (code_base/arithmetic.py:124-125): probability exactly 0
     if (tid == 0) {
       int remax = 0;
@@ -214,10 +268,10 @@ __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t*
         const float4 v = w4[c];
         const int b = 4 * c - mis;
         u64 p;
-        p = pack_of(v.x, b); pm = p > pm ? p : pm;
-        p = pack_of(v.y, b + 1); pm = p > pm ? p : pm;
-        p = pack_of(v.z, b + 2); pm = p > pm ? p : pm;
-        p = pack_of(v.w, b + 3); pm = p > pm ? p : pm;
+        p = pack_of(v.x + 0.0f, b); pm = p > pm ? p : pm;
+        p = pack_of(v.y + 0.0f, b + 1); pm = p > pm ? p : pm;
+        p = pack_of(v.z + 0.0f, b + 2); pm = p > pm ? p : pm;
+        p = pack_of(v.w + 0.0f, b + 3); pm = p > pm ? p : pm;
       }
       pm = f_reduce_u(pm, OpMaxU(), sc->red);
       M = key_of_pack(pm);
@@ -257,7 +311,7 @@ __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t*
       sc->bail = bail;
     }
     __syncthreads();
-    if (sc->bail) { if (tid == 0) hand_over(P, slow_ws, row); continue; }
+    if (sc->bail) { if (tid == 0) hand_over(P, slow_ws, row, F_WHY_EST); continue; }
     const float kappa_hi = sc->kappa_hi, kappa_lo = sc->kappa_lo, clamp_key = sc->clamp_key;
 
     auto a_of = [&](float key) -> double {                  // (double(x)/temp) - (double(max)/temp), :128-130
@@ -265,38 +319,47 @@ __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t*
       if (!UNIT_TEMP) x = __ddiv_rn(x, temp);
       return x - dm;
     };
+    auto band_push = [&](int id, double e) {
+      const int s = atomicAdd(&sc->band_n, 1);
+      if (s < F_BAND_CAP) { band[s].id = id; band[s].kept = 0; band[s].e = e; }
+    };
 
     // ------------------------------------------------------------------ P1: the fp64 exp pass
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0, accl = 0.0;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    double accl0 = 0.0, accl1 = 0.0, accl2 = 0.0, accl3 = 0.0;
     int cnt_hi = 0;
-#define F_P1(KEY, OUT, ID, ACC)                                             \
-    do {                                                                      \
-      const double e_ = ns_exp64_core(a_of(KEY), tab);                        \
-      (ACC) += e_;                                                            \
-      if ((KEY) >= kappa_hi) { cnt_hi++; (OUT) = __double2float_rz(e_); }     \
-      else {                                                                  \
-        (OUT) = 0.0f;                                                         \
-        if ((KEY) < kappa_lo) accl += e_;                                     \
-        else {                                                                \
-          const int s_ = atomicAdd(&sc->band_n, 1);                           \
-          if (s_ < F_BAND_CAP) { band[s_].id = (ID); band[s_].kept = 0; band[s_].e = e_; } \
-        }                                                                     \
-      }                                                                       \
-    } while (0)
     for (int c = tid; c < W4; c += FT) {
       const float4 v = w4[c];
       const int b = 4 * c - mis;
+      const double e0 = ns_exp64_core(a_of(v.x), tab);
+      const double e1 = ns_exp64_core(a_of(v.y), tab);
+      const double e2 = ns_exp64_core(a_of(v.z), tab);
+      const double e3 = ns_exp64_core(a_of(v.w), tab);
+      acc0 += e0; acc1 += e1; acc2 += e2; acc3 += e3;
+      const bool h0 = v.x >= kappa_hi, h1 = v.y >= kappa_hi, h2 = v.z >= kappa_hi, h3 = v.w >= kappa_hi;
+      const bool l0 = v.x < kappa_lo, l1 = v.y < kappa_lo, l2 = v.z < kappa_lo, l3 = v.w < kappa_lo;
+      if (l0) accl0 += e0;
+      if (l1) accl1 += e1;
+      if (l2) accl2 += e2;
+      if (l3) accl3 += e3;
+      cnt_hi += (int)h0 + (int)h1 + (int)h2 + (int)h3;
       float4 o;
-      F_P1(v.x, o.x, b, acc0);
-      F_P1(v.y, o.y, b + 1, acc1);
-      F_P1(v.z, o.z, b + 2, acc2);
-      F_P1(v.w, o.w, b + 3, acc3);
+      o.x = h0 ? __double2float_rz(e0) : 0.0f;
+      o.y = h1 ? __double2float_rz(e1) : 0.0f;
+      o.z = h2 ? __double2float_rz(e2) : 0.0f;
+      o.w = h3 ? __double2float_rz(e3) : 0.0f;
       w4[c] = o;
+      if (!((h0 | l0) & (h1 | l1) & (h2 | l2) & (h3 | l3))) {   // rare: inside the guard band
+        if (!(h0 | l0)) band_push(b, e0);
+        if (!(h1 | l1)) band_push(b + 1, e1);
+        if (!(h2 | l2)) band_push(b + 2, e2);
+        if (!(h3 | l3)) band_push(b + 3, e3);
+      }
     }
-#undef F_P1
-    const double sum_all = f_sum_d((acc0 + acc1) + (acc2 + acc3), sc->red);   // softmax normaliser, :130
-    const double sum_lo = f_sum_d(accl, sc->red);
-    const u64 n_hi = f_reduce_u((u64)cnt_hi, OpAddU(), sc->red);
+    double sum_all = (acc0 + acc1) + (acc2 + acc3);          // softmax normaliser, :130
+    double sum_lo = (accl0 + accl1) + (accl2 + accl3);
+    u64 n_hi = (u64)cnt_hi;
+    f_sum_ddu(sum_all, sum_lo, n_hi, sc->red);
     const double inv = __ddiv_rn(1.0, sum_all);
     const int nband = sc->band_n;
     const double band_scale = scalbn(1.0, 52 - sc->band_E);
@@ -309,17 +372,20 @@ __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t*
       my_band_kept = k ? 1 : 0;
       if (!k) atomicAdd(&sc->band_cut_int, (u64)__double2ull_rz(e * band_scale));   // exact, order-free
     }
+    const float kappa_lo_pred = nextafterf(kappa_lo, -INFINITY);
     if (tid == 0) {
       // the provisional split is valid iff exp is monotone and both band edges classify as assumed
       const double e_hi = ns_exp64_core(a_of(kappa_hi), tab);
-      const double e_lo = ns_exp64_core(a_of(nextafterf(kappa_lo, -INFINITY)), tab);
-      int bail = (nband > F_BAND_CAP) || !((e_hi * inv) >= thr) || ((e_lo * inv) >= thr);
+      const double e_lo = ns_exp64_core(a_of(kappa_lo_pred), tab);
+      int bail = 0;
+      if (nband > F_BAND_CAP) bail = F_WHY_BAND;
+      else if (!((e_hi * inv) >= thr) || ((e_lo * inv) >= thr)) bail = F_WHY_VERIFY;
       sc->bail = bail;
     }
-    const u64 n_band_kept = f_reduce_u((u64)my_band_kept, OpAddU(), sc->red);   // (syncs inside)
+    const u64 n_band_kept = f_reduce_u((u64)my_band_kept, OpAddU(), sc->red);   // (barriers inside)
     const u64 cand = n_hi + n_band_kept;
     if (sc->bail || !(cand >= 2 && cand <= (u64)P.topk)) {   // rank form (top-k inside the cutoff set) -> exact kernel
-      if (tid == 0) hand_over(P, slow_ws, row);
+      if (tid == 0) hand_over(P, slow_ws, row, sc->bail ? sc->bail : F_WHY_RANK);
       continue;
     }
     const double sum_bc = (double)sc->band_cut_int * scalbn(1.0, sc->band_E - 52);
@@ -330,132 +396,175 @@ __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t*
     // bucket shift: every kept element (certain or band) has e >= e(kappa_lo_pred) > 0
     int SH;
     {
-      const float e_min = __double2float_rz(ns_exp64_core(a_of(nextafterf(kappa_lo, -INFINITY)), tab));
+      const float e_min = __double2float_rz(ns_exp64_core(a_of(kappa_lo_pred), tab));
       const uint32_t span = F_TOP - __float_as_uint(e_min);
       SH = 0;
       while ((span >> SH) > (uint32_t)(F_NB - 1)) ++SH;
     }
     auto bin_of_e = [&](float e32) -> uint32_t { return (F_TOP - __float_as_uint(e32)) >> SH; };
+    // exact bin width from the original logit (same formula as the exact kernel)
+    auto exact_mass = [&](int id) -> uint32_t {
+      const float key = g[id] + 0.0f;
+      return (uint32_t)__double2ll_rn(ns_exp64_core(a_of(key), tab) * C);
+    };
+    // bin width decided from the truncated e alone; returns false when it is not decidable
+    auto quick_mass = [&](float e32, uint32_t* q) -> bool {
+      const double ed = (double)e32;
+      const uint32_t ql = (uint32_t)ns_double_as_u64(__fma_rn(ed, C_lo, magic));
+      const uint32_t qh = (uint32_t)ns_double_as_u64(__fma_rn(ed, C_hi, magic));
+      *q = ql;
+      return ql == qh;
+    };
 
     // ------------------------------------------------------------------ P2: integer bin widths
-    u64 qacc = 0;
-#define F_P2(E32, ID)                                                        \
-    do {                                                                      \
-      if ((E32) > 0.0f) {                                                     \
-        const double ed_ = (double)(E32);                                     \
-        const uint32_t ql_ = (uint32_t)ns_double_as_u64(__fma_rn(ed_, C_lo, magic)); \
-        const uint32_t qh_ = (uint32_t)ns_double_as_u64(__fma_rn(ed_, C_hi, magic)); \
-        if (ql_ == qh_) { atomicAdd(&hist[bin_of_e(E32)], ql_); qacc += ql_; } \
-        else { const int s_ = atomicAdd(&sc->u_n, 1); if (s_ < F_U_CAP) ulist[s_] = (ID); } \
-      }                                                                       \
-    } while (0)
     for (int c = tid; c < W4; c += FT) {
       const float4 v = w4[c];
       const int b = 4 * c - mis;
-      F_P2(v.x, b); F_P2(v.y, b + 1); F_P2(v.z, b + 2); F_P2(v.w, b + 3);
+      uint32_t q0, q1, q2, q3;
+      const bool k0 = quick_mass(v.x, &q0), k1 = quick_mass(v.y, &q1), k2 = quick_mass(v.z, &q2), k3 = quick_mass(v.w, &q3);
+      if (k0 & k1 & k2 & k3) {                               // e32 == 0 (not kept) yields q == 0: skipped
+        if (q0) atomicAdd(&hist[bin_of_e(v.x)], q0);
+        if (q1) atomicAdd(&hist[bin_of_e(v.y)], q1);
+        if (q2) atomicAdd(&hist[bin_of_e(v.z)], q2);
+        if (q3) atomicAdd(&hist[bin_of_e(v.w)], q3);
+      } else {
+        const float ev[4] = {v.x, v.y, v.z, v.w};
+        const uint32_t qv[4] = {q0, q1, q2, q3};
+        const bool kv[4] = {k0, k1, k2, k3};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (kv[j]) { if (qv[j]) atomicAdd(&hist[bin_of_e(ev[j])], qv[j]); }
+          else { const int s = atomicAdd(&sc->u_n, 1); if (s < F_U_CAP) ulist[s] = b + j; }
+        }
+      }
     }
-#undef F_P2
     __syncthreads();
     const int nu = sc->u_n;
-    if (nu > F_U_CAP) { if (tid == 0) hand_over(P, slow_ws, row); continue; }
-    // exact bin width from the original logit (same formula as the exact kernel)
-    auto exact_mass = [&](int id) -> u64 {
-      const float key = g[id] + 0.0f;
-      return (u64)__double2ll_rn(ns_exp64_core(a_of(key), tab) * C);
-    };
+    if (nu > F_U_CAP) { if (tid == 0) hand_over(P, slow_ws, row, F_WHY_ULIST); continue; }
     for (int u = tid; u < nu; u += FT) {
       const int id = ulist[u];
-      const u64 q = exact_mass(id);
-      atomicAdd(&hist[bin_of_e(words[id + mis])], (uint32_t)q);
-      qacc += q;
+      atomicAdd(&hist[bin_of_e(words[id + mis])], exact_mass(id));
     }
     if (tid < nband && band[tid].kept) {
       const double e = band[tid].e;
-      const u64 q = (u64)__double2ll_rn(e * C);
-      atomicAdd(&hist[bin_of_e(__double2float_rz(e))], (uint32_t)q);
-      qacc += q;
+      atomicAdd(&hist[bin_of_e(__double2float_rz(e))], (uint32_t)__double2ll_rn(e * C));
     }
-    const u64 Q = f_reduce_u(qacc, OpAddU(), sc->red);
     __syncthreads();
 
-    // ------------------------------------------------------------------ SEL helpers
-    // bucket of bucket-prefix search: first bucket whose inclusive prefix exceeds tau
-    auto locate = [&](u64 tau) {
-      constexpr int BPT = F_NB / FT;
+    // ------------------------------------------------------------------ SEL: bucket scan, kept in registers
+    u64 hloc[F_BPT];
+    u64 hexcl;                                               // mass in all buckets before this thread's first one
+    u64 Q;
+    {
       const int lane = tid & 31, warp = tid >> 5;
-      u64 local[BPT];
       u64 tsum = 0;
 #pragma unroll
-      for (int b = 0; b < BPT; ++b) { local[b] = hist[tid * BPT + b]; tsum += local[b]; }
+      for (int b = 0; b < F_BPT; ++b) { hloc[b] = hist[tid * F_BPT + b]; tsum += hloc[b]; }
       u64 inc = tsum;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const u64 t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += t;
       }
-      __syncthreads();
       if (lane == 31) sc->red[warp] = inc;
+      __syncthreads();
+      u64 woff = 0, tot = 0;
+#pragma unroll
+      for (int w = 0; w < FW; ++w) { const u64 x = sc->red[w]; if (w < warp) woff += x; tot += x; }
+      hexcl = woff + inc - tsum;
+      Q = tot;
+    }
+    // first bucket whose inclusive prefix exceeds tau -> sc->sel_bin / sel_prefix
+    auto locate = [&](u64 tau) {
       if (tid == 0) { sc->sel_bin = -1; sc->sel_prefix = 0; }
       __syncthreads();
-      u64 woff = 0;
-      for (int w = 0; w < warp; ++w) woff += sc->red[w];
-      u64 excl = woff + inc - tsum;
+      u64 excl = hexcl;
 #pragma unroll
-      for (int b = 0; b < BPT; ++b) {
-        if (local[b] != 0 && excl <= tau && tau < excl + local[b]) { sc->sel_bin = tid * BPT + b; sc->sel_prefix = excl; }
-        excl += local[b];
+      for (int b = 0; b < F_BPT; ++b) {
+        if (hloc[b] != 0 && excl <= tau && tau < excl + hloc[b]) { sc->sel_bin = tid * F_BPT + b; sc->sel_prefix = excl; }
+        excl += hloc[b];
       }
       __syncthreads();
     };
-    // mass in all buckets before bucket tb
-    auto prefix_of = [&](int tb) -> u64 {
-      constexpr int BPT = F_NB / FT;
-      u64 s = 0;
+    // mass in all buckets before bucket tb -> sc->sel_prefix
+    auto prefix_of = [&](int tb) {
+      __syncthreads();
+      if (tb >= tid * F_BPT && tb < (tid + 1) * F_BPT) {
+        u64 excl = hexcl;
+        const int off = tb - tid * F_BPT;
 #pragma unroll
-      for (int b = 0; b < BPT; ++b) { const int idx = tid * BPT + b; if (idx < tb) s += hist[idx]; }
-      return f_reduce_u(s, OpAddU(), sc->red);
+        for (int b = 0; b < F_BPT; ++b) if (b < off) excl += hloc[b];
+        sc->sel_prefix = excl;
+      }
+      __syncthreads();
     };
-    // gather bucket tb: exact order key (original logit, id) and exact mass of every kept element in it
+    // gather bucket tb: every kept element in it with its exact mass
     auto collect = [&](int tb) -> int {
       if (tid == 0) sc->c_n = 0;
       __syncthreads();
       for (int c = tid; c < W4; c += FT) {
         const float4 v = w4[c];
-        const int b = 4 * c - mis;
-        const float ev[4] = {v.x, v.y, v.z, v.w};
+        const bool m0 = bin_of_e(v.x) == (uint32_t)tb, m1 = bin_of_e(v.y) == (uint32_t)tb;
+        const bool m2 = bin_of_e(v.z) == (uint32_t)tb, m3 = bin_of_e(v.w) == (uint32_t)tb;
+        if (m0 | m1 | m2 | m3) {                             // e32 == 0 maps far outside the histogram
+          const float ev[4] = {v.x, v.y, v.z, v.w};
+          const bool mv[4] = {m0, m1, m2, m3};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (bin_of_e(ev[j]) == (uint32_t)tb) {              // e32 == 0 maps far outside the histogram
-            const int id = b + j;
-            const int s = atomicAdd(&sc->c_n, 1);
-            if (s < F_C_CAP) { clist[s].pack = pack_of(g[id] + 0.0f, id); clist[s].w = exact_mass(id); }
+          for (int j = 0; j < 4; ++j) {
+            if (mv[j]) {
+              const int id = 4 * c - mis + j;
+              uint32_t q;
+              if (!quick_mass(ev[j], &q)) q = exact_mass(id);
+              const int s = atomicAdd(&sc->c_n, 1);
+              if (s < F_C_CAP) { clist[s].ebits = __float_as_uint(ev[j]); clist[s].id = id; clist[s].w = q; clist[s].key = 0.0f; }
+            }
           }
         }
       }
-      if (tid < nband && band[tid].kept && bin_of_e(__double2float_rz(band[tid].e)) == (uint32_t)tb) {
-        const int id = band[tid].id;
-        const int s = atomicAdd(&sc->c_n, 1);
-        if (s < F_C_CAP) { clist[s].pack = pack_of(g[id] + 0.0f, id); clist[s].w = (u64)__double2ll_rn(band[tid].e * C); }
+      if (tid < nband && band[tid].kept) {
+        const float e32 = __double2float_rz(band[tid].e);
+        if (bin_of_e(e32) == (uint32_t)tb) {
+          const int s = atomicAdd(&sc->c_n, 1);
+          if (s < F_C_CAP) {
+            clist[s].ebits = __float_as_uint(e32); clist[s].id = band[tid].id;
+            clist[s].w = (uint32_t)__double2ll_rn(band[tid].e * C); clist[s].key = 0.0f;
+          }
+        }
       }
       __syncthreads();
       int n = sc->c_n;
       if (n > F_C_CAP) { n = F_C_CAP; if (tid == 0 && P.status) atomicOr(&P.status[row], NS_ST_BIN_OVERFLOW); }
+      // entries sharing a truncated e need the original logit to be ordered
+      for (int c = tid; c < n; c += FT) {
+        const uint32_t eb = clist[c].ebits;
+        bool dup = false;
+        for (int o = 0; o < n; ++o) dup |= (o != c) && (clist[o].ebits == eb);
+        if (dup) clist[c].key = g[clist[c].id] + 0.0f;
+      }
+      __syncthreads();
       return n;
     };
-    // exact position inside the gathered bucket: by cumulative target tau, or of a given token id
+    // coder order: larger e first; equal truncated e: larger logit first; equal logits: lower id first
+    auto cand_before = [&](const CandEntry& x, const CandEntry& y) -> bool {
+      if (x.ebits != y.ebits) return x.ebits > y.ebits;
+      if (x.key != y.key) return x.key > y.key;
+      return x.id < y.id;
+    };
     auto resolve = [&](int n, u64 prefix, bool by_token, u64 tau, int want_id) -> bool {
       if (tid == 0) sc->res_found = 0;
       __syncthreads();
       for (int c = tid; c < n; c += FT) {
-        const u64 pc = clist[c].pack, wc = clist[c].w;
+        const CandEntry me = clist[c];
         u64 before = prefix;
-        for (int o = 0; o < n; ++o) if (clist[o].pack > pc) before += clist[o].w;
-        const bool hit = by_token ? (id_of_pack(pc) == want_id) : (wc != 0 && before <= tau && tau < before + wc);
-        if (hit) { sc->res_idx = id_of_pack(pc); sc->res_before = before; sc->res_w = wc; sc->res_found = 1; }
+        for (int o = 0; o < n; ++o) {
+          const CandEntry ot = clist[o];
+          if (o != c && cand_before(ot, me)) before += ot.w;
+        }
+        const bool hit = by_token ? (me.id == want_id) : (me.w != 0 && before <= tau && tau < before + me.w);
+        if (hit) { sc->res_idx = me.id; sc->res_before = before; sc->res_w = me.w; sc->res_found = 1; }
       }
       __syncthreads();
-      const bool f = sc->res_found != 0;
-      return f;
+      return sc->res_found != 0;
     };
     auto select_tau = [&](u64 tau, int* idx, u64* before, u64* w) -> bool {
       locate(tau);
@@ -472,11 +581,16 @@ __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t*
     // ------------------------------------------------------------------ overfill (:153-158)
     u64 slack;
     bool truncated = false;
-    u64 trunc_pack = 0;
+    CandEntry trunc_e = {0u, 0, 0u, 0.0f};
     if (Q > R) {
       int j; u64 bj, wj;
-      if (select_tau(R, &j, &bj, &wj)) { truncated = true; trunc_pack = pack_of(g[j] + 0.0f, j); slack = R - bj; }
-      else slack = 0;
+      if (select_tau(R, &j, &bj, &wj)) {
+        truncated = true;
+        trunc_e.ebits = __float_as_uint(words[j + mis]);
+        for (int k = 0; k < nband; ++k) if (band[k].id == j) trunc_e.ebits = __float_as_uint(__double2float_rz(band[k].e));
+        trunc_e.id = j; trunc_e.key = g[j] + 0.0f;
+        slack = R - bj;
+      } else slack = 0;
     } else {
       slack = R - Q;
     }
@@ -505,23 +619,27 @@ __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t*
       int tok = P.token_in[(size_t)row * P.token_stride + slot];
       if (tok < 0 || tok >= V) tok = top_id;
       // is the observed token in the kept set, and in which bucket?
-      const float e32t = words[tok + mis];
-      int tb = -1;
-      if (e32t > 0.0f) tb = (int)bin_of_e(e32t);
-      else {
+      float e32t = words[tok + mis];
+      if (!(e32t > 0.0f)) {
         for (int k = 0; k < nband; ++k)
-          if (band[k].id == tok && band[k].kept) tb = (int)bin_of_e(__double2float_rz(band[k].e));
+          if (band[k].id == tok && band[k].kept) e32t = __double2float_rz(band[k].e);
       }
-      bool in_range = tb >= 0;
+      bool in_range = e32t > 0.0f;
       u64 bs = 0, ws = top_mass;
       int token = top_id;
       if (in_range) {
-        const u64 pref = prefix_of(tb);
+        const int tb = (int)bin_of_e(e32t);
+        prefix_of(tb);
+        const u64 pref = sc->sel_prefix;
         const int n = collect(tb);
         if (resolve(n, pref, true, 0, tok)) { bs = sc->res_before; ws = sc->res_w; token = tok; }
         else in_range = false;
         __syncthreads();
-        if (in_range && truncated && !(pack_of(g[tok] + 0.0f, tok) > trunc_pack)) { in_range = false; token = top_id; bs = 0; ws = top_mass; }
+        if (in_range && truncated) {
+          CandEntry me = {__float_as_uint(e32t), tok, 0u, g[tok] + 0.0f};
+          const CandEntry tr = trunc_e;
+          if (!cand_before(me, tr)) { in_range = false; token = top_id; bs = 0; ws = top_mass; }
+        }
       }
       if (token == top_id) { nb = lo; nt = lo + ws + slack; }   // :342 / :347-348
       else { nb = lo + bs + slack; nt = nb + ws; }
@@ -529,4 +647,3 @@ __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t*
     }
   }
 }
-#undef F_ONLINE

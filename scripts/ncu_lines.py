@@ -59,3 +59,46 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def regions(sass_csv, dis, kern, bounds):
+    """Attribute instructions/samples to program regions given as {name: (first_line, last_line)} of the
+    kernel's own source file; helper-header lines inherit the region of the last kernel-file line seen."""
+    rows = list(csv.reader(open(sass_csv)))
+    for i, r in enumerate(rows[:6]):
+        if "Source" in r and "Address" in r:
+            hdr, start = r, i + 1
+            break
+    ci, cs = hdr.index("Instructions Executed"), hdr.index("# Samples")
+    sass = [(int(r[ci] or 0), int(r[cs] or 0)) for r in rows[start:] if len(r) > ci]
+    lines = open(dis).read().split("\n")
+    in_k, cur, per = False, None, []
+    main_file = None
+    for ln in lines:
+        if ln.startswith(".text.") and ln.endswith(":"):
+            in_k = kern in ln
+            continue
+        if not in_k:
+            continue
+        m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
+        if m:
+            f = m.group(1).split("/")[-1]
+            if main_file is None:
+                main_file = f
+            if f == bounds["_file"]:
+                cur = int(m.group(2))
+            continue
+        if re.match(r"\s*/\*([0-9a-f]+)\*/\s+(.*);", ln):
+            per.append(cur)
+    agg = defaultdict(lambda: [0, 0])
+    for k in range(min(len(sass), len(per))):
+        name = "other"
+        for nm, rng in bounds.items():
+            if nm != "_file" and per[k] is not None and rng[0] <= per[k] <= rng[1]:
+                name = nm
+        agg[name][0] += sass[k][0]
+        agg[name][1] += sass[k][1]
+    ti = sum(v[0] for v in agg.values()) or 1
+    ts = sum(v[1] for v in agg.values()) or 1
+    for nm, v in agg.items():
+        print("%-10s inst %10d %5.1f%%   samples %7d %5.1f%%" % (nm, v[0], 100.0 * v[0] / ti, v[1], 100.0 * v[1] / ts))
