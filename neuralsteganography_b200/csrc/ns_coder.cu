@@ -202,9 +202,7 @@ enum { MODE_ENC = 0, MODE_DEC = 1, MODE_DEBUG = 2 };
 // ---- per-stream epilogues (one thread) ---------------------------------------------------------
 // encode: consume the shared prefix, rescale, emit the token (code_base/arithmetic.py:179-203)
 __device__ __forceinline__ void finish_encode(const ns_ac_params& P, int row, int slot, int token,
-                                              u64 nb, u64 nt, u64 k0, u64 Q) {
-  const int cursor = P.cursor[row];
-  const int mlen = P.msg_len[row];
+                                              u64 nb, u64 nt, u64 k0, u64 Q, int cursor, int mlen) {
   uint64_t nlo, nhi;
   const int n = ns_interval_update(nb, nt, P.precision, &nlo, &nhi);   // :179-190
   P.lo[row] = nlo; P.hi[row] = nhi;
@@ -522,7 +520,7 @@ __device__ void ac_exact_row(const ns_ac_params& P, const int row, u64* dbg_q, u
       if (s == top_id) { nb = lo; nt = lo + ws + slack; }
       else { nb = lo + bs + slack; nt = nb + ws; }           // :175-176
     }
-    if (tid == 0) finish_encode(P, row, slot, token, nb, nt, k0, Q);
+    if (tid == 0) finish_encode(P, row, slot, token, nb, nt, k0, Q, cursor, mlen);
   } else {
     // decode: rank of the observed token = mass in front of it (:298)
     const u64 wt = rm.mass(keys[tok], tok);

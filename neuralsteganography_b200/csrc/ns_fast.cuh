@@ -37,7 +37,15 @@ enum { F_WHY_EST = 1, F_WHY_BAND = 2, F_WHY_VERIFY = 3, F_WHY_RANK = 4, F_WHY_UL
 struct BandEntry { int id; int kept; double e; };
 struct CandEntry { uint32_t ebits; int id; uint32_t w; float key; };   // 16 B
 
+// per-row scalars, fetched one row ahead by a helper lane so no global latency sits on the row's path
+struct RowMeta {
+  u64 lo, hi, window;
+  int slot, cursor, mlen, tok;
+  int phase, pad;
+};
+
 struct FScal {
+  RowMeta meta[2];
   u64 red[3 * FW];
   u64 bar[F_PIECES];                 // mbarriers of the row copy
   float sum32; int remax; float M; int top_id;
@@ -141,47 +149,54 @@ __device__ __forceinline__ void f_sum_ddu(double& a, double& b, u64& c, u64* scr
   a = ra; b = rb; c = rc;
 }
 
-template <bool UNIT_TEMP, int MODE>
-__global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t* slow_ws) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* tab = reinterpret_cast<double*>(smem_raw);
-  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + NS_EXP_N * 8);
-  BandEntry* band = reinterpret_cast<BandEntry*>(smem_raw + NS_EXP_N * 8 + F_NB * 4);
-  int* ulist = reinterpret_cast<int*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16);
-  CandEntry* clist = reinterpret_cast<CandEntry*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16 + F_U_CAP * 4);
-  FScal* sc = reinterpret_cast<FScal*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16 + F_U_CAP * 4 + F_C_CAP * 16);
-  float* words = reinterpret_cast<float*>(smem_raw + FIXED_BYTES);   // element id lives at words[id + mis]
-  float4* w4 = reinterpret_cast<float4*>(words);
+struct FastSmem {
+  double* tab; uint32_t* hist; BandEntry* band; int* ulist; CandEntry* clist; FScal* sc; float* words;
+};
 
+__device__ __forceinline__ RowMeta f_load_meta(const ns_ac_params& P, int row, int mode) {
+  RowMeta m;
+  m.phase = P.phase ? (int)P.phase[row] : NS_PHASE_CODING;
+  m.slot = P.ntok ? P.ntok[row] : 0;
+  m.lo = P.lo[row]; m.hi = P.hi[row];
+  m.cursor = 0; m.mlen = 0; m.window = 0; m.tok = -1; m.pad = 0;
+  if (mode == MODE_ENC) {
+    m.cursor = P.cursor[row];
+    m.mlen = P.msg_len[row];
+    m.window = ns_read_bits(P.msg + (size_t)row * P.msg_stride, m.cursor, m.mlen, P.precision);   // :168-171
+  } else {
+    const int total = P.ntok_total ? P.ntok_total[row] : 0x7fffffff;
+    m.mlen = total;
+    if (m.slot < total) m.tok = P.token_in[(size_t)row * P.token_stride + m.slot];
+  }
+  return m;
+}
+
+template <bool UNIT_TEMP, int MODE>
+__device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws, const int row, const RowMeta meta,
+                                         const FastSmem sm, uint32_t& parity) {
+  double* tab = sm.tab; uint32_t* hist = sm.hist; BandEntry* band = sm.band; int* ulist = sm.ulist;
+  CandEntry* clist = sm.clist; FScal* sc = sm.sc; float* words = sm.words;
+  float4* w4 = reinterpret_cast<float4*>(words);
   const int tid = threadIdx.x;
   const int V = P.V;
   const double temp = P.temp;
   const float c2 = (float)(1.4426950408889634 / temp);     // log2(e)/temp for the fp32 estimate
   const double magic = 6755399441055744.0;                 // 1.5 * 2^52
-
-  for (int i = tid; i < NS_EXP_N; i += FT) tab[i] = c_exp_tab[i];
-  if (tid == 0) {
-    for (int k = 0; k < F_PIECES; ++k) f_mbar_init(&sc->bar[k], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  uint32_t parity = 0;                                     // bit k: phase parity of piece k's mbarrier
-
-  for (int row = blockIdx.x; row < P.B; row += gridDim.x) {
-    __syncthreads();                                       // previous row is finished with shared memory
-    uint8_t phase = P.phase ? P.phase[row] : (uint8_t)NS_PHASE_CODING;
-    if (phase == NS_PHASE_DONE) continue;
-    if (MODE != MODE_ENC) phase = NS_PHASE_CODING;
-    const int slot = P.ntok ? P.ntok[row] : 0;
+  int phase = meta.phase;
+  if (phase == NS_PHASE_DONE) return;
+  if (MODE != MODE_ENC) phase = NS_PHASE_CODING;
+  const int slot = meta.slot;
+  {
     if (MODE == MODE_ENC && P.ntok && slot >= P.token_cap) {
       if (tid == 0) {
         if (P.phase) P.phase[row] = NS_PHASE_DONE;
         if (P.status) atomicOr(&P.status[row], NS_ST_TOKEN_OVERFLOW);
       }
-      continue;
+      return;
     }
-    if (MODE == MODE_DEC && P.ntok_total && slot >= P.ntok_total[row]) {
+    if (MODE == MODE_DEC && P.ntok_total && slot >= meta.mlen) {
       if (tid == 0 && P.phase) P.phase[row] = NS_PHASE_DONE;
-      continue;
+      return;
     }
 
     // ------------------------------------------------------------------ L: bulk copy + estimate
@@ -222,16 +237,17 @@ __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t*
       }
     }
     // fp32 online softmax over the pieces as they land: (tm, ts) per thread, lowest id of the max
-    float tm = -3.0e38f, ts = 0.f;
+    float tm = -3.0e38f, ts = 0.f, ntc = 3.0e38f * c2;     // ntc = -tm * c2
     int ti = 0;
     auto online4 = [&](const float4 v, const int b) {
       const float cm = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
       if (cm > tm) {
         ts *= f_ex2((tm - cm) * c2);
         tm = cm;
+        ntc = -cm * c2;
         ti = (v.x == cm) ? b : (v.y == cm) ? b + 1 : (v.z == cm) ? b + 2 : b + 3;
       }
-      ts += (f_ex2((v.x - tm) * c2) + f_ex2((v.y - tm) * c2)) + (f_ex2((v.z - tm) * c2) + f_ex2((v.w - tm) * c2));
+      ts += (f_ex2(fmaf(v.x, c2, ntc)) + f_ex2(fmaf(v.y, c2, ntc))) + (f_ex2(fmaf(v.z, c2, ntc)) + f_ex2(fmaf(v.w, c2, ntc)));
     };
     for (int k = 0; k < F_PIECES; ++k) {
       const int c0 = 1 + k * PC;
@@ -289,11 +305,11 @@ __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t*
 
     if (MODE == MODE_ENC && phase == NS_PHASE_TAIL) {
       if (tid == 0) finish_tail(P, row, slot, top_id);
-      continue;
+      return;
     }
 
     // ------------------------------------------------------------------ row constants
-    const u64 lo = P.lo[row], hi = P.hi[row];
+    const u64 lo = meta.lo, hi = meta.hi;
     const u64 R = hi - lo;                                   // arithmetic.py:140
     const double thr = __ddiv_rn(1.0, (double)R);            // :141
     const double Md = (double)M;
@@ -311,7 +327,7 @@ __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t*
       sc->bail = bail;
     }
     __syncthreads();
-    if (sc->bail) { if (tid == 0) hand_over(P, slow_ws, row, F_WHY_EST); continue; }
+    if (sc->bail) { if (tid == 0) hand_over(P, slow_ws, row, F_WHY_EST); return; }
     const float kappa_hi = sc->kappa_hi, kappa_lo = sc->kappa_lo, clamp_key = sc->clamp_key;
 
     auto a_of = [&](float key) -> double {                  // (double(x)/temp) - (double(max)/temp), :128-130
@@ -328,6 +344,7 @@ __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t*
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
     double accl0 = 0.0, accl1 = 0.0, accl2 = 0.0, accl3 = 0.0;
     int cnt_hi = 0;
+    const bool need_count = P.topk < V;                      // otherwise only "at least 2 kept" matters
     for (int c = tid; c < W4; c += FT) {
       const float4 v = w4[c];
       const int b = 4 * c - mis;
@@ -338,11 +355,11 @@ __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t*
       acc0 += e0; acc1 += e1; acc2 += e2; acc3 += e3;
       const bool h0 = v.x >= kappa_hi, h1 = v.y >= kappa_hi, h2 = v.z >= kappa_hi, h3 = v.w >= kappa_hi;
       const bool l0 = v.x < kappa_lo, l1 = v.y < kappa_lo, l2 = v.z < kappa_lo, l3 = v.w < kappa_lo;
-      if (l0) accl0 += e0;
-      if (l1) accl1 += e1;
-      if (l2) accl2 += e2;
-      if (l3) accl3 += e3;
-      cnt_hi += (int)h0 + (int)h1 + (int)h2 + (int)h3;
+      accl0 = __fma_rn(e0, l0 ? 1.0 : 0.0, accl0);           // exact: e * {0,1} + acc
+      accl1 = __fma_rn(e1, l1 ? 1.0 : 0.0, accl1);
+      accl2 = __fma_rn(e2, l2 ? 1.0 : 0.0, accl2);
+      accl3 = __fma_rn(e3, l3 ? 1.0 : 0.0, accl3);
+      if (need_count) cnt_hi += (int)h0 + (int)h1 + (int)h2 + (int)h3;
       float4 o;
       o.x = h0 ? __double2float_rz(e0) : 0.0f;
       o.y = h1 ? __double2float_rz(e1) : 0.0f;
@@ -383,13 +400,16 @@ __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t*
       sc->bail = bail;
     }
     const u64 n_band_kept = f_reduce_u((u64)my_band_kept, OpAddU(), sc->red);   // (barriers inside)
-    const u64 cand = n_hi + n_band_kept;
-    if (sc->bail || !(cand >= 2 && cand <= (u64)P.topk)) {   // rank form (top-k inside the cutoff set) -> exact kernel
-      if (tid == 0) hand_over(P, slow_ws, row, sc->bail ? sc->bail : F_WHY_RANK);
-      continue;
-    }
+    const u64 cand = n_hi + n_band_kept;                     // only counted when topk < V
     const double sum_bc = (double)sc->band_cut_int * scalbn(1.0, sc->band_E - 52);
     const double S = (sum_all - sum_lo) - sum_bc;            // sum of the kept e_i
+    // kept set must have 2..topk members, else the reference switches to rank form (:75).  The row
+    // maximum has e == 1 exactly, so "another token is kept" <=> S > 1 (its e is >= thr*sum >= 2^-31).
+    const bool form_ok = need_count ? (cand >= 2 && cand <= (u64)P.topk) : ((inv >= thr) && (S > 1.0));
+    if (sc->bail || !form_ok) {                              // rank form (top-k inside the cutoff set) -> exact kernel
+      if (tid == 0) hand_over(P, slow_ws, row, sc->bail ? sc->bail : F_WHY_RANK);
+      return;
+    }
     const double C = __ddiv_rn((double)R, S);                // :146
     const double C_lo = C * (1.0 - 2.220446049250313e-16);
     const double C_hi = C * (1.0 + 1.1920928955078125e-07 + 9.094947017729282e-13);
@@ -440,7 +460,7 @@ __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t*
     }
     __syncthreads();
     const int nu = sc->u_n;
-    if (nu > F_U_CAP) { if (tid == 0) hand_over(P, slow_ws, row, F_WHY_ULIST); continue; }
+    if (nu > F_U_CAP) { if (tid == 0) hand_over(P, slow_ws, row, F_WHY_ULIST); return; }
     for (int u = tid; u < nu; u += FT) {
       const int id = ulist[u];
       atomicAdd(&hist[bin_of_e(words[id + mis])], exact_mass(id));
@@ -597,10 +617,7 @@ __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t*
     const u64 top_mass = (u64)__double2ll_rn(C);             // e of the row maximum is exactly 1
     u64 nb, nt;
     if (MODE == MODE_ENC) {
-      const int cursor = P.cursor[row];
-      const int mlen = P.msg_len[row];
-      const u64 window = ns_read_bits(P.msg + (size_t)row * P.msg_stride, cursor, mlen, P.precision);  // :168-171
-      const u64 m_rel = window - lo;
+      const u64 m_rel = meta.window - lo;                    // next `precision` message bits (:168-171)
       int token;
       if (m_rel < top_mass + slack) {                        // rank 0 absorbs the slack (:158)
         token = top_id; nb = lo; nt = lo + top_mass + slack;
@@ -614,9 +631,9 @@ __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t*
         if (s == top_id) { nb = lo; nt = lo + ws + slack; }
         else { nb = lo + bs + slack; nt = nb + ws; }         // :175-176
       }
-      if (tid == 0) finish_encode(P, row, slot, token, nb, nt, cand, Q);
+      if (tid == 0) finish_encode(P, row, slot, token, nb, nt, cand, Q, meta.cursor, meta.mlen);
     } else {
-      int tok = P.token_in[(size_t)row * P.token_stride + slot];
+      int tok = meta.tok;
       if (tok < 0 || tok >= V) tok = top_id;
       // is the observed token in the kept set, and in which bucket?
       float e32t = words[tok + mis];
@@ -645,5 +662,38 @@ __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t*
       else { nb = lo + bs + slack; nt = nb + ws; }
       if (tid == 0) finish_decode(P, row, slot, in_range, nb, nt, cand, Q);
     }
+  }
+}
+
+template <bool UNIT_TEMP, int MODE>
+__global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t* slow_ws) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FastSmem sm;
+  sm.tab = reinterpret_cast<double*>(smem_raw);
+  sm.hist = reinterpret_cast<uint32_t*>(smem_raw + NS_EXP_N * 8);
+  sm.band = reinterpret_cast<BandEntry*>(smem_raw + NS_EXP_N * 8 + F_NB * 4);
+  sm.ulist = reinterpret_cast<int*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16);
+  sm.clist = reinterpret_cast<CandEntry*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16 + F_U_CAP * 4);
+  sm.sc = reinterpret_cast<FScal*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16 + F_U_CAP * 4 + F_C_CAP * 16);
+  sm.words = reinterpret_cast<float*>(smem_raw + FIXED_BYTES);   // element id lives at words[id + mis]
+  const int tid = threadIdx.x;
+  constexpr int HELPER = FT - 32;                          // lane that fetches the next row's scalars
+  for (int i = tid; i < NS_EXP_N; i += FT) sm.tab[i] = c_exp_tab[i];
+  if (tid == 0) {
+    for (int k = 0; k < F_PIECES; ++k) f_mbar_init(&sm.sc->bar[k], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid == HELPER && (int)blockIdx.x < P.B) sm.sc->meta[0] = f_load_meta(P, blockIdx.x, MODE);
+  uint32_t parity = 0;                                     // bit k: phase parity of piece k's mbarrier
+  int it = 0;
+  for (int row = blockIdx.x; row < P.B; row += gridDim.x, ++it) {
+    __syncthreads();                                       // previous row is finished with shared memory
+    const RowMeta meta = sm.sc->meta[it & 1];
+    RowMeta next;
+    const int nrow = row + gridDim.x;
+    const bool fetch = (tid == HELPER) && (nrow < P.B);
+    if (fetch) next = f_load_meta(P, nrow, MODE);          // loads in flight while the row is processed
+    fast_row<UNIT_TEMP, MODE>(P, slow_ws, row, meta, sm, parity);
+    if (fetch) sm.sc->meta[(it + 1) & 1] = next;
   }
 }

@@ -62,8 +62,14 @@ NS_HD double ns_exp64_core(double a, const double* __restrict__ tab) {
   double p = ns_fma(q, r2, r);
   double e = ns_fma(T, p, T);
   // scale by 2^k through the exponent field (result stays normal for a >= -708)
+#if defined(__CUDA_ARCH__)
+  (void)k;
+  const int hi = __double2hiint(e) + ((n & ~(NS_EXP_N - 1)) << (20 - NS_EXP_L));   // high word += k << 20
+  return __hiloint2double(hi, __double2loint(e));
+#else
   uint64_t bits = ns_double_as_u64(e) + ((uint64_t)(int64_t)k << 52);
   return ns_u64_as_double(bits);
+#endif
 }
 
 // exp(a) for any a <= 0: exactly 0 below -708 (also for the -inf mask and NaN).

@@ -51,6 +51,8 @@ def test_golden_cases_bit_exact(golden_dir, cases, force_exact):
             assert not took_exact                                  # nothing was handed over: exact kernel only
         elif cfg["name"] == "ac_v50257_p26_full_t10":
             assert not took_exact, cfg["name"]                    # config-3 rows stay on the throughput kernel
+        elif cfg["topk"] < 1000:
+            assert took_exact, cfg["name"]                        # top-k inside the cutoff set -> exact kernel
         for s in range(S):
             assert toks[s] == data["tokens_%d" % s].tolist(), (cfg["name"], s, "tokens")
             want = data["trace_%d" % s][:, :5]                 # new_bottom, new_top, nbits, lo, hi
@@ -143,7 +145,8 @@ def test_fast_and_exact_kernels_agree():
     for temp in (1.0, 0.8):
         a = [o for o in outs if o[1] == temp and not o[0]][0]
         b = [o for o in outs if o[1] == temp and o[0]][0]
-        assert a[6] == 0                                            # throughput kernel handled every row itself
+        # hand-overs only happen where the interval has collapsed (fewer than 2 tokens above 1/range)
+        assert a[6] < 0.25 * B * 24
         for k in (2, 3, 4, 5):
             assert torch.equal(a[k], b[k]), (temp, k)
 
