@@ -32,7 +32,7 @@ constexpr float F_BAND_EPS = 0.0009765625f;   // 2^-10 half-width (in log units)
 constexpr uint32_t F_TOP = 0x3F800000u;       // bit pattern of 1.0f = e of the row maximum
 
 // hand-over reasons (status bits 8..15, diagnostics only)
-enum { F_WHY_EST = 1, F_WHY_BAND = 2, F_WHY_VERIFY = 3, F_WHY_RANK = 4, F_WHY_ULIST = 5 };
+enum { F_WHY_EST = 1, F_WHY_BAND = 2, F_WHY_VERIFY = 3, F_WHY_RANK = 4, F_WHY_ULIST = 5, F_WHY_BUCKET = 6 };
 
 struct BandEntry { int id; int kept; double e; };
 struct CandEntry { uint32_t ebits; int id; uint32_t w; float key; };   // 16 B
@@ -238,9 +238,11 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     }
     // fp32 online softmax over the pieces as they land: (tm, ts) per thread, lowest id of the max
     float tm = -3.0e38f, ts = 0.f, ntc = 3.0e38f * c2;     // ntc = -tm * c2
+    float kmin = 3.0e38f;                                  // lowest logit of the row (bucket range)
     int ti = 0;
     auto online4 = [&](const float4 v, const int b) {
       const float cm = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+      kmin = fminf(kmin, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
       if (cm > tm) {
         ts *= f_ex2((tm - cm) * c2);
         tm = cm;
@@ -257,12 +259,25 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       for (int c = c0 + tid; c < c1; c += FT) online4(w4[c], 4 * c - mis);
     }
     __syncthreads();                                       // edge chunks written by threads 0..7
-    if (tid == 0) online4(w4[0], -mis);
-    if (tid == 32) online4(w4[W4 - 1], 4 * (W4 - 1) - mis);
+    {
+      const float keep = kmin;                             // the edge chunks carry -inf padding: not part of the range
+      if (tid == 0) online4(w4[0], -mis);
+      if (tid == 32) online4(w4[W4 - 1], 4 * (W4 - 1) - mis);
+      kmin = keep;
+      if (tid == 0 || tid == 32) {
+        const float4 v = tid == 0 ? w4[0] : w4[W4 - 1];
+        if (v.x > -INFINITY) kmin = fminf(kmin, v.x);
+        if (v.y > -INFINITY) kmin = fminf(kmin, v.y);
+        if (v.z > -INFINITY) kmin = fminf(kmin, v.z);
+        if (v.w > -INFINITY) kmin = fminf(kmin, v.w);
+      }
+    }
     const u64 pmax = f_reduce_u(pack_of(tm + 0.0f, ti), OpMaxU(), sc->red);
     float M = key_of_pack(pmax);
     int top_id = id_of_pack(pmax);
     float ssum = f_sum_f(ts * f_ex2((tm - M) * c2), sc->red);
+    // lowest interior logit (-inf if the caller masked tokens with -inf: then the cutoff bounds the range)
+    const float key_min = key_of_pack(f_reduce_u(pack_of(kmin, 0), OpMinU(), sc->red));
     // forbidden tokens (code_base/arithmetic.py:124-125): probability exactly 0
     if (tid == 0) {
       int remax = 0;
@@ -404,8 +419,10 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     const double sum_bc = (double)sc->band_cut_int * scalbn(1.0, sc->band_E - 52);
     const double S = (sum_all - sum_lo) - sum_bc;            // sum of the kept e_i
     // kept set must have 2..topk members, else the reference switches to rank form (:75).  The row
-    // maximum has e == 1 exactly, so "another token is kept" <=> S > 1 (its e is >= thr*sum >= 2^-31).
-    const bool form_ok = need_count ? (cand >= 2 && cand <= (u64)P.topk) : ((inv >= thr) && (S > 1.0));
+    // maximum has e == 1 exactly and any other kept token has e >= thr * sum_all >= thr, while the
+    // rounding error of S is a few ulp of sum_all (< 2^-36 thr-units at precision 31): "another
+    // token is kept" <=> S > 1 + thr/2.
+    const bool form_ok = need_count ? (cand >= 2 && cand <= (u64)P.topk) : ((inv >= thr) && (S > 1.0 + 0.5 * thr));
     if (sc->bail || !form_ok) {                              // rank form (top-k inside the cutoff set) -> exact kernel
       if (tid == 0) hand_over(P, slow_ws, row, sc->bail ? sc->bail : F_WHY_RANK);
       return;
@@ -413,10 +430,10 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     const double C = __ddiv_rn((double)R, S);                // :146
     const double C_lo = C * (1.0 - 2.220446049250313e-16);
     const double C_hi = C * (1.0 + 1.1920928955078125e-07 + 9.094947017729282e-13);
-    // bucket shift: every kept element (certain or band) has e >= e(kappa_lo_pred) > 0
+    // bucket shift: every kept element (certain or band) has e >= e(max(kappa_lo_pred, lowest logit)) > 0
     int SH;
     {
-      const float e_min = __double2float_rz(ns_exp64_core(a_of(kappa_lo_pred), tab));
+      const float e_min = __double2float_rz(ns_exp64_core(a_of(fmaxf(kappa_lo_pred, key_min)), tab));
       const uint32_t span = F_TOP - __float_as_uint(e_min);
       SH = 0;
       while ((span >> SH) > (uint32_t)(F_NB - 1)) ++SH;
@@ -553,7 +570,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       }
       __syncthreads();
       int n = sc->c_n;
-      if (n > F_C_CAP) { n = F_C_CAP; if (tid == 0 && P.status) atomicOr(&P.status[row], NS_ST_BIN_OVERFLOW); }
+      if (n > F_C_CAP) return -1;                            // dense bucket: the exact kernel redoes the row
       // entries sharing a truncated e need the original logit to be ordered
       for (int c = tid; c < n; c += FT) {
         const uint32_t eb = clist[c].ebits;
@@ -586,12 +603,14 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       __syncthreads();
       return sc->res_found != 0;
     };
+    bool overflow = false;                                   // a gathered bucket did not fit (uniform across the CTA)
     auto select_tau = [&](u64 tau, int* idx, u64* before, u64* w) -> bool {
       locate(tau);
       const int tb = sc->sel_bin;
       const u64 pref = sc->sel_prefix;
       if (tb < 0) return false;
       const int n = collect(tb);
+      if (n < 0) { overflow = true; return false; }
       const bool f = resolve(n, pref, false, tau, 0);
       *idx = sc->res_idx; *before = sc->res_before; *w = sc->res_w;
       __syncthreads();
@@ -614,6 +633,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     } else {
       slack = R - Q;
     }
+    if (overflow) { if (tid == 0) hand_over(P, slow_ws, row, F_WHY_BUCKET); return; }
     const u64 top_mass = (u64)__double2ll_rn(C);             // e of the row maximum is exactly 1
     u64 nb, nt;
     if (MODE == MODE_ENC) {
@@ -624,6 +644,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       } else {
         int s; u64 bs, ws;
         if (!select_tau(m_rel - slack, &s, &bs, &ws)) {
+          if (overflow) { if (tid == 0) hand_over(P, slow_ws, row, F_WHY_BUCKET); return; }
           s = top_id; bs = 0; ws = top_mass;
           if (tid == 0 && P.status) atomicOr(&P.status[row], NS_ST_BIN_OVERFLOW);
         }
@@ -649,6 +670,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
         prefix_of(tb);
         const u64 pref = sc->sel_prefix;
         const int n = collect(tb);
+        if (n < 0) { if (tid == 0) hand_over(P, slow_ws, row, F_WHY_BUCKET); return; }
         if (resolve(n, pref, true, 0, tok)) { bs = sc->res_before; ws = sc->res_w; token = tok; }
         else in_range = false;
         __syncthreads();

@@ -15,6 +15,7 @@ for scale_fn, name in ((lambda p: 1.0 + 0.5 * p, "scales 1..3"), (lambda p: 3.0,
         hist = {}
         for t in range(24):
             st.status.zero_()
+            lo0 = st.lo.cpu().numpy().copy(); hi0 = st.hi.cpu().numpy().copy(); ph0 = st.phase.cpu().numpy().copy()
             st.encode_step(pool[t % T])
             torch.cuda.synchronize()
             s = st.status.cpu().numpy()
@@ -23,5 +24,6 @@ for scale_fn, name in ((lambda p: 1.0 + 0.5 * p, "scales 1..3"), (lambda p: 3.0,
                 why = int(s[r]) >> 8
                 hist[why] = hist.get(why, 0) + 1
                 if hist[why] <= 2:
-                    print("   row", r, "step", t, "why", why, "status", hex(int(s[r])))
+                    print("   row", r, "step", t, "why", why, "status", hex(int(s[r])), "R", int(hi0[r] - lo0[r]), "lo", int(lo0[r]), "phase", int(ph0[r]),
+                          "cursor", int(st.cursor[r]), "len", len(msgs[r]))
         print(name, "temp", temp, "hand-over reasons {why: count}:", hist)
