@@ -104,6 +104,9 @@ typedef struct ns_ac_params {
      only.  force_exact != 0 also selects the exact kernel only. */
   int32_t* slow_ws;
   int32_t force_exact;
+  /* optional profiling counters (16 x uint64, zeroed by the caller): SM-clock cycles spent per
+     phase of the throughput kernel, summed over thread 0 of every CTA; [15] counts rows */
+  uint64_t* prof;
 } ns_ac_params;
 
 int ns_version(void);

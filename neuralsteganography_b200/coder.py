@@ -160,6 +160,7 @@ class ArithmeticStreams:
         p.trace = N.ptr(self.trace)
         p.slow_ws = self.slow_ws.data_ptr()
         p.force_exact = int(self.force_exact)
+        p.prof = N.ptr(getattr(self, "prof", None))
         return p
 
     def encode_step(self, logits: torch.Tensor) -> None:

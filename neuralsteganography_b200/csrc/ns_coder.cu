@@ -46,7 +46,8 @@ struct Scalars {
   int res_found;
 };
 
-constexpr int FIXED_BYTES = NS_EXP_N * 8 + HIST_BYTES + LIST_CAP * (int)sizeof(ListEntry) + 1024;
+constexpr int FIXED_BYTES = 26624;    // exp table, histogram, lists, scalars (both kernels); the row follows
+static_assert(NS_EXP_N * 8 + HIST_BYTES + LIST_CAP * (int)sizeof(ListEntry) + 1024 <= FIXED_BYTES, "exact smem layout");
 static_assert(sizeof(Scalars) <= 1024, "scalar block too large");
 constexpr int MAX_VOCAB = (SMEM_LIMIT - FIXED_BYTES) / 4 - 8;
 

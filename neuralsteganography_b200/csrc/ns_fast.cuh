@@ -55,8 +55,8 @@ struct FScal {
   int res_idx; u64 res_before; u64 res_w; int res_found;
   float kappa_lo, kappa_hi, clamp_key; int band_E;
 };
-static_assert(sizeof(FScal) <= 1024, "FScal too large");
-static_assert(NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16 + F_U_CAP * 4 + F_C_CAP * 16 + 1024 <= FIXED_BYTES, "fast smem layout");
+static_assert(sizeof(FScal) <= 2048, "FScal too large");
+static_assert(NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16 + F_U_CAP * 4 + 2 * F_C_CAP * 16 + 2048 <= FIXED_BYTES, "fast smem layout");
 
 __device__ __forceinline__ float f_ex2(float x) {
   float y;
@@ -89,6 +89,12 @@ __device__ __forceinline__ void f_mbar_wait(u64* bar, uint32_t parity) {
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t"
       "}\n" :: "r"(f_smem_addr(bar)), "r"(parity) : "memory");
+}
+
+// hist[bin] += q unless q == 0, as one predicated shared-memory reduction (no branch)
+__device__ __forceinline__ void f_hist_add(uint32_t* hist, uint32_t bin, uint32_t q) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}"
+               :: "r"(f_smem_addr(hist + bin)), "r"(q) : "memory");
 }
 
 // queue a row for the exact kernel: slow_ws = {count, done, rows...}
@@ -171,9 +177,16 @@ __device__ __forceinline__ RowMeta f_load_meta(const ns_ac_params& P, int row, i
   return m;
 }
 
+// phase timers (thread 0 only, active when P.prof is given)
+struct PhaseClock {
+  bool on; long long last; u64 acc[16];
+  __device__ __forceinline__ void start() { if (on) last = clock64(); }
+  __device__ __forceinline__ void mark(int k) { if (on) { const long long t = clock64(); acc[k] += (u64)(t - last); last = t; } }
+};
+
 template <bool UNIT_TEMP, int MODE>
 __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws, const int row, const RowMeta meta,
-                                         const FastSmem sm, uint32_t& parity) {
+                                         const FastSmem sm, uint32_t& parity, PhaseClock& pc) {
   double* tab = sm.tab; uint32_t* hist = sm.hist; BandEntry* band = sm.band; int* ulist = sm.ulist;
   CandEntry* clist = sm.clist; FScal* sc = sm.sc; float* words = sm.words;
   float4* w4 = reinterpret_cast<float4*>(words);
@@ -236,6 +249,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
         for (int off = tid * 128; off < nbytes; off += FT * 128) f_prefetch_l2(np + off);
       }
     }
+    pc.mark(0);                                            // row prologue: copy issue, edges, prefetch
     // fp32 online softmax over the pieces as they land: (tm, ts) per thread, lowest id of the max
     float tm = -3.0e38f, ts = 0.f, ntc = 3.0e38f * c2;     // ntc = -tm * c2
     float kmin = 3.0e38f;                                  // lowest logit of the row (bucket range)
@@ -258,6 +272,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       if (c0 < c1) { f_mbar_wait(&sc->bar[k], (parity >> k) & 1u); parity ^= (1u << k); }
       for (int c = c0 + tid; c < c1; c += FT) online4(w4[c], 4 * c - mis);
     }
+    pc.mark(1);                                            // L: waits + estimate over the pieces
     __syncthreads();                                       // edge chunks written by threads 0..7
     {
       const float keep = kmin;                             // the edge chunks carry -inf padding: not part of the range
@@ -355,6 +370,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       if (s < F_BAND_CAP) { band[s].id = id; band[s].kept = 0; band[s].e = e; }
     };
 
+    pc.mark(2);                                            // reductions, masks, row constants
     // ------------------------------------------------------------------ P1: the fp64 exp pass
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
     double accl0 = 0.0, accl1 = 0.0, accl2 = 0.0, accl3 = 0.0;
@@ -388,6 +404,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
         if (!(h3 | l3)) band_push(b + 3, e3);
       }
     }
+    pc.mark(3);                                            // P1 loop
     double sum_all = (acc0 + acc1) + (acc2 + acc3);          // softmax normaliser, :130
     double sum_lo = (accl0 + accl1) + (accl2 + accl3);
     u64 n_hi = (u64)cnt_hi;
@@ -453,6 +470,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       return ql == qh;
     };
 
+    pc.mark(4);                                            // FIX: sums, band, verification, constants
     // ------------------------------------------------------------------ P2: integer bin widths
     for (int c = tid; c < W4; c += FT) {
       const float4 v = w4[c];
@@ -460,10 +478,10 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       uint32_t q0, q1, q2, q3;
       const bool k0 = quick_mass(v.x, &q0), k1 = quick_mass(v.y, &q1), k2 = quick_mass(v.z, &q2), k3 = quick_mass(v.w, &q3);
       if (k0 & k1 & k2 & k3) {                               // e32 == 0 (not kept) yields q == 0: skipped
-        if (q0) atomicAdd(&hist[bin_of_e(v.x)], q0);
-        if (q1) atomicAdd(&hist[bin_of_e(v.y)], q1);
-        if (q2) atomicAdd(&hist[bin_of_e(v.z)], q2);
-        if (q3) atomicAdd(&hist[bin_of_e(v.w)], q3);
+        f_hist_add(hist, bin_of_e(v.x) & (F_NB - 1), q0);    // q == 0 (not kept): predicated off
+        f_hist_add(hist, bin_of_e(v.y) & (F_NB - 1), q1);
+        f_hist_add(hist, bin_of_e(v.z) & (F_NB - 1), q2);
+        f_hist_add(hist, bin_of_e(v.w) & (F_NB - 1), q3);
       } else {
         const float ev[4] = {v.x, v.y, v.z, v.w};
         const uint32_t qv[4] = {q0, q1, q2, q3};
@@ -475,6 +493,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
         }
       }
     }
+    pc.mark(5);                                            // P2 loop
     __syncthreads();
     const int nu = sc->u_n;
     if (nu > F_U_CAP) { if (tid == 0) hand_over(P, slow_ws, row, F_WHY_ULIST); return; }
@@ -511,6 +530,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       hexcl = woff + inc - tsum;
       Q = tot;
     }
+    pc.mark(6);                                            // undecided/band fix-ups, bucket scan
     // first bucket whose inclusive prefix exceeds tau -> sc->sel_bin / sel_prefix
     auto locate = [&](u64 tau) {
       if (tid == 0) { sc->sel_bin = -1; sc->sel_prefix = 0; }
@@ -633,6 +653,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     } else {
       slack = R - Q;
     }
+    pc.mark(7);                                            // overfill selection
     if (overflow) { if (tid == 0) hand_over(P, slow_ws, row, F_WHY_BUCKET); return; }
     const u64 top_mass = (u64)__double2ll_rn(C);             // e of the row maximum is exactly 1
     u64 nb, nt;
@@ -652,7 +673,9 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
         if (s == top_id) { nb = lo; nt = lo + ws + slack; }
         else { nb = lo + bs + slack; nt = nb + ws; }         // :175-176
       }
+      pc.mark(8);                                          // target selection
       if (tid == 0) finish_encode(P, row, slot, token, nb, nt, cand, Q, meta.cursor, meta.mlen);
+      pc.mark(9);
     } else {
       int tok = meta.tok;
       if (tok < 0 || tok >= V) tok = top_id;
@@ -682,7 +705,9 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       }
       if (token == top_id) { nb = lo; nt = lo + ws + slack; }   // :342 / :347-348
       else { nb = lo + bs + slack; nt = nb + ws; }
+      pc.mark(8);
       if (tid == 0) finish_decode(P, row, slot, in_range, nb, nt, cand, Q);
+      pc.mark(9);
     }
   }
 }
@@ -696,7 +721,7 @@ __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t*
   sm.band = reinterpret_cast<BandEntry*>(smem_raw + NS_EXP_N * 8 + F_NB * 4);
   sm.ulist = reinterpret_cast<int*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16);
   sm.clist = reinterpret_cast<CandEntry*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16 + F_U_CAP * 4);
-  sm.sc = reinterpret_cast<FScal*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16 + F_U_CAP * 4 + F_C_CAP * 16);
+  sm.sc = reinterpret_cast<FScal*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16 + F_U_CAP * 4 + 2 * F_C_CAP * 16);
   sm.words = reinterpret_cast<float*>(smem_raw + FIXED_BYTES);   // element id lives at words[id + mis]
   const int tid = threadIdx.x;
   constexpr int HELPER = FT - 32;                          // lane that fetches the next row's scalars
@@ -707,15 +732,23 @@ __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t*
   }
   if (tid == HELPER && (int)blockIdx.x < P.B) sm.sc->meta[0] = f_load_meta(P, blockIdx.x, MODE);
   uint32_t parity = 0;                                     // bit k: phase parity of piece k's mbarrier
+  PhaseClock pc;
+  pc.on = (P.prof != nullptr) && tid == 0;
+  pc.last = 0;
+  for (int k = 0; k < 16; ++k) pc.acc[k] = 0;
   int it = 0;
   for (int row = blockIdx.x; row < P.B; row += gridDim.x, ++it) {
+    pc.start();
     __syncthreads();                                       // previous row is finished with shared memory
+    pc.mark(10);                                           // waiting for the previous row's stragglers
     const RowMeta meta = sm.sc->meta[it & 1];
     RowMeta next;
     const int nrow = row + gridDim.x;
     const bool fetch = (tid == HELPER) && (nrow < P.B);
     if (fetch) next = f_load_meta(P, nrow, MODE);          // loads in flight while the row is processed
-    fast_row<UNIT_TEMP, MODE>(P, slow_ws, row, meta, sm, parity);
+    fast_row<UNIT_TEMP, MODE>(P, slow_ws, row, meta, sm, parity, pc);
     if (fetch) sm.sc->meta[(it + 1) & 1] = next;
+    if (pc.on) pc.acc[15] += 1;
   }
+  if (pc.on) for (int k = 0; k < 16; ++k) atomicAdd((unsigned long long*)&P.prof[k], (unsigned long long)pc.acc[k]);
 }

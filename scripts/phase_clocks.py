@@ -1,0 +1,29 @@
+"""Per-phase SM-clock cycles of the throughput kernel at the bench configuration (thread 0 of every CTA)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from neuralsteganography_b200.coder import ArithmeticStreams
+V, B, P = 50257, int(os.environ.get("STREAMS", "4096")), 2
+g = torch.Generator(device="cuda").manual_seed(1234)
+pool = [torch.randn(B, V, generator=g, device="cuda") * 3.0 for _ in range(P)]
+rng = np.random.default_rng(0)
+words = rng.integers(0, 1 << 32, size=(B, 130), dtype=np.uint64).astype(np.uint32)
+names = ["prologue", "L wait+estimate", "reduce+consts", "P1 exp pass", "FIX", "P2 q pass", "fixups+scan", "overfill sel",
+         "target sel", "epilogue", "row-top barrier"]
+for mode in ("enc", "dec"):
+    st = ArithmeticStreams(B, V, precision=26, temp=1.0, topk=V, token_cap=32)
+    st.set_packed_messages(torch.from_numpy(words.view(np.int32)), torch.full((B,), 4096, dtype=torch.int32))
+    for t in range(3): st.encode_step(pool[t % P])
+    if mode == "dec":
+        toks, n = st.tokens.clone(), st.ntok.clone()
+        st = ArithmeticStreams(B, V, precision=26, temp=1.0, topk=V, token_cap=32)
+        st.set_token_tensor(toks, n)
+    st.prof = torch.zeros(16, dtype=torch.int64, device="cuda")
+    step = st.encode_step if mode == "enc" else st.decode_step
+    for t in range(3): step(pool[t % P])
+    torch.cuda.synchronize()
+    pr = st.prof.cpu().numpy().astype(np.float64)
+    rows = pr[15]
+    print(mode, "rows", int(rows), "cycles/row total %.0f" % (pr[:11].sum() / rows))
+    for k, nm in enumerate(names):
+        print("   %-18s %8.0f cyc/row %5.1f%%" % (nm, pr[k] / rows, 100 * pr[k] / pr[:11].sum()))
