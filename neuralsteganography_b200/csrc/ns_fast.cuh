@@ -26,7 +26,7 @@ constexpr int F_BPT = F_NB / FT;     // buckets per thread in the scan
 constexpr int F_BAND_CAP = 128;
 constexpr int F_U_CAP = 256;
 constexpr int F_C_CAP = 256;
-constexpr int F_PIECES = 8;          // bulk-copy pieces per row
+constexpr int F_PIECES = 9;          // bulk-copy pieces per row (3 * FT float4 each, 24 KB)
 constexpr int F_MIN_VOCAB = 256;     // below this the exact kernel is used
 constexpr float F_BAND_EPS = 0.0009765625f;   // 2^-10 half-width (in log units) of the exact-list band
 constexpr uint32_t F_TOP = 0x3F800000u;       // bit pattern of 1.0f = e of the row maximum
@@ -217,7 +217,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     const int mis = (int)(((uintptr_t)g & 15u) >> 2);
     const int W4 = (mis + V + 3) >> 2;                     // float4 chunks of the padded row
     const int NI = W4 - 2;                                 // interior chunks: wholly inside the row
-    const int PC = (NI + F_PIECES - 1) / F_PIECES;         // chunks per piece
+    const int PC = 3 * FT;                                 // chunks per piece: every thread does 3 of each piece
     if (tid == 0) {
       // generic-proxy accesses of the previous row are ordered before the async-proxy writes
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
