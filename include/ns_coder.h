@@ -125,6 +125,56 @@ int ns_ac_decode_step(const ns_ac_params* p, void* cuda_stream);
    (code_base/arithmetic.py:146-158) */
 int ns_ac_debug_bins(const ns_ac_params* p, uint64_t* q_out, uint64_t* meta_out, void* cuda_stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Comparison codecs of the reference, same batching and token bookkeeping as ns_ac_params:
+ *   rank    src/neuralstego/codec/arithmetic.py:122-231 (encode_with_lm / decode_with_lm),
+ *           :370-385 (_rank_tokens); temperature as in lm/arithmetic.py:69-73
+ *   huffman code_base/huffman_baseline.py:7-71, :73-165; code_base/huffman.py:12-76
+ *   bins    code_base/block_baseline.py:9-24, :26-97, :99-189
+ * Message / output bits are packed like ns_ac_params.msg: bit t of a stream is the t-th element
+ * of the reference's Python bit list.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ns_codec_params {
+  const float* logits;      /* fp32 [B, V], row stride ld */
+  int64_t ld;
+  int32_t B;
+  int32_t V;
+  double temp;              /* rank: temperature of the provider (lm/arithmetic.py:72) */
+  int32_t param;            /* huffman: bits_per_word (1..9); bins: block_size; rank: unused */
+  int32_t topk;             /* rank: quality top_k (quality.py:76-81); <= 0 = none */
+  int32_t mask_id[2];       /* huffman/bins: tokens forced to -1e10 (huffman_baseline.py:26-27); -1 = none */
+  uint8_t* phase;           /* NS_PHASE_CODING / NS_PHASE_DONE per stream; may be NULL */
+  int32_t* status;          /* NS_ST_* bits; may be NULL */
+  int32_t* ntok;            /* per-stream token slot, as in ns_ac_params */
+  int32_t token_cap;
+  const int32_t* ntok_total;
+  const uint32_t* msg;      /* encode */
+  int64_t msg_stride;
+  const int32_t* msg_len;
+  int32_t* cursor;
+  int32_t* token_out;
+  int64_t token_stride;
+  const int32_t* token_in;  /* decode */
+  uint32_t* out_bits;
+  int64_t out_stride;
+  int32_t* out_len;
+  const int32_t* total_bits; /* rank decode: payload bit count (state["residual_bits"], arithmetic.py:167) */
+  uint8_t* nbits_out;       /* bits consumed / emitted this step; may be NULL */
+  const int32_t* lut;       /* bins: word -> bin [V] (get_bins, block_baseline.py:9-24) */
+} ns_codec_params;
+
+int ns_sizeof_codec_params(void);
+const char* ns_codec_last_error_string(void);
+/* (B) rank codec: floor(log2(#tokens with p>0)) message bits pick the token of that rank */
+int ns_rank_encode_step(const ns_codec_params* p, void* cuda_stream);
+int ns_rank_decode_step(const ns_codec_params* p, void* cuda_stream);
+/* Huffman baseline over the top 2^bits_per_word tokens (heapq-compatible tree) */
+int ns_huffman_encode_step(const ns_codec_params* p, void* cuda_stream);
+int ns_huffman_decode_step(const ns_codec_params* p, void* cuda_stream);
+/* bins baseline: block_size message bits pick a vocabulary bin, token = argmax inside it */
+int ns_bins_encode_step(const ns_codec_params* p, void* cuda_stream);
+int ns_bins_decode_step(const ns_codec_params* p, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,11 +59,12 @@ class CodecParams(C.Structure):
         ("temp", C.c_double), ("param", C.c_int32), ("topk", C.c_int32),
         ("mask_id", C.c_int32 * 2),
         ("phase", C.c_void_p), ("status", C.c_void_p),
+        ("ntok", C.c_void_p), ("token_cap", C.c_int32), ("ntok_total", C.c_void_p),
         ("msg", C.c_void_p), ("msg_stride", C.c_int64), ("msg_len", C.c_void_p),
         ("cursor", C.c_void_p), ("token_out", C.c_void_p), ("token_stride", C.c_int64),
         ("token_in", C.c_void_p),
         ("out_bits", C.c_void_p), ("out_stride", C.c_int64), ("out_len", C.c_void_p),
-        ("nbits_out", C.c_void_p), ("lut", C.c_void_p), ("lut2", C.c_void_p),
+        ("total_bits", C.c_void_p), ("nbits_out", C.c_void_p), ("lut", C.c_void_p),
     ]
 
 
@@ -86,6 +87,9 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.ns_version.restype = C.c_int
     lib.ns_last_error_string.restype = C.c_char_p
     lib.ns_ac_max_vocab.restype = C.c_int
+    lib.ns_sizeof_ac_params.restype = C.c_int
+    if hasattr(lib, "ns_sizeof_codec_params"):
+        lib.ns_sizeof_codec_params.restype = C.c_int
     for name in ("ns_ac_encode_step", "ns_ac_decode_step"):
         fn = getattr(lib, name)
         fn.argtypes = [C.POINTER(AcParams), C.c_void_p]

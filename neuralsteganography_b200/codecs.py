@@ -1,0 +1,163 @@
+"""Batched device drivers of the reference's comparison codecs (rank, Huffman, bins).
+
+Host mirrors of
+  * ``encode_with_lm`` / ``decode_with_lm``  src/neuralstego/codec/arithmetic.py:122-231
+  * ``encode_huffman`` / ``decode_huffman``  code_base/huffman_baseline.py:7-71, :73-165
+  * ``get_bins`` / ``encode_block`` / ``decode_block``  code_base/block_baseline.py:9-24, :26-97, :99-189
+with the per-token work in ``csrc/ns_codecs.cu`` behind the C ABI (``ns_codec_params``).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .coder import NEWLINE2_ID, pack_bits, unpack_bits
+
+
+def get_bins(vocab_size: int, block_size: int):
+    """``bin2words, words2bin`` exactly as the reference builds them (block_baseline.py:9-24):
+    numpy's legacy generator seeded with the block size shuffles ``arange(vocab)``, the shuffled
+    ids are cut into ``2**block_size`` equal bins.  Returns (list of id arrays, int32 [V] table;
+    ids the reference's integer truncation leaves out of every bin map to -1)."""
+    num_bins = 2 ** block_size
+    words_per_bin = vocab_size / num_bins
+    ordering = np.arange(vocab_size)
+    state = np.random.get_state()
+    try:
+        np.random.seed(block_size)
+        np.random.shuffle(ordering)
+    finally:
+        np.random.set_state(state)
+    bin2words = [ordering[int(i * words_per_bin): int((i + 1) * words_per_bin)] for i in range(num_bins)]
+    word2bin = np.full(vocab_size, -1, dtype=np.int32)
+    for j, words in enumerate(bin2words):
+        word2bin[words] = j
+    return bin2words, word2bin
+
+
+class CodecStreams:
+    """B streams of one comparison codec.  ``kind`` in {"rank", "huffman", "bins"}."""
+
+    def __init__(self, kind: str, batch: int, vocab: int, *, param: int = 0, temp: float = 1.0,
+                 topk: int = 0, device="cuda", token_cap: int = 1024, mask_ids: Optional[Sequence[int]] = None):
+        if kind not in ("rank", "huffman", "bins"):
+            raise ValueError("unknown codec kind: %s" % kind)
+        self.lib = N.load()
+        if not torch.cuda.is_available():
+            raise N.NativeLibraryError("no CUDA device: the codecs have no CPU fallback")
+        self.kind, self.B, self.V = kind, int(batch), int(vocab)
+        self.param, self.temp, self.topk = int(param), float(temp), int(topk)
+        self.device = torch.device(device)
+        if mask_ids is None:
+            # the baselines forbid the same two tokens as the arithmetic coder; the rank codec none
+            mask_ids = (-1, -1) if kind == "rank" else (vocab - 1, NEWLINE2_ID if vocab > NEWLINE2_ID else -1)
+        self.mask_ids = tuple(int(x) for x in mask_ids)
+        self.token_cap = int(token_cap)
+        d = self.device
+        self.phase = torch.zeros(self.B, dtype=torch.uint8, device=d)
+        self.status = torch.zeros(self.B, dtype=torch.int32, device=d)
+        self.ntok = torch.zeros(self.B, dtype=torch.int32, device=d)
+        self.cursor = torch.zeros(self.B, dtype=torch.int32, device=d)
+        self.nbits = torch.zeros(self.B, dtype=torch.uint8, device=d)
+        self.tokens = torch.full((self.B, self.token_cap), -1, dtype=torch.int32, device=d)
+        self.lut = None
+        if kind == "bins":
+            _, w2b = get_bins(self.V, self.param)
+            self.lut = torch.from_numpy(w2b).to(d)
+        self.msg = self.msg_len = self.ntok_total = self.out_bits = self.out_len = self.total_bits = None
+        self._p = N.CodecParams()
+        self._enc = getattr(self.lib, "ns_%s_encode_step" % kind)
+        self._dec = getattr(self.lib, "ns_%s_decode_step" % kind)
+
+    # ------------------------------------------------------------------ setup
+    def set_messages(self, bit_lists: Sequence[Sequence[int]]) -> None:
+        words, lens = pack_bits(bit_lists)
+        self.msg = torch.from_numpy(words.view(np.int32)).to(self.device)
+        self.msg_len = torch.from_numpy(lens).to(self.device)
+        self.status.zero_(); self.ntok.zero_(); self.cursor.zero_()
+        self.tokens.fill_(-1)
+        self.phase.copy_(torch.where(self.msg_len > 0, 0, 2).to(torch.uint8))
+
+    def set_tokens(self, token_lists: Sequence[Sequence[int]], total_bits: Optional[Sequence[int]] = None) -> None:
+        lens = np.array([len(t) for t in token_lists], dtype=np.int32)
+        cap = max(self.token_cap, int(lens.max()) if self.B else 1)
+        tk = np.full((self.B, cap), -1, dtype=np.int32)
+        for r, t in enumerate(token_lists):
+            tk[r, : len(t)] = np.asarray(t, dtype=np.int32)
+        self.tokens = torch.from_numpy(tk).to(self.device)
+        self.token_cap = cap
+        self.ntok_total = torch.from_numpy(lens).to(self.device)
+        self.status.zero_(); self.ntok.zero_(); self.cursor.zero_()
+        self.phase.copy_(torch.where(self.ntok_total > 0, 0, 2).to(torch.uint8))
+        words = (cap * 32 + 31) // 32 + 2
+        self.out_bits = torch.zeros((self.B, words), dtype=torch.int32, device=self.device)
+        self.out_len = torch.zeros(self.B, dtype=torch.int32, device=self.device)
+        self.total_bits = None
+        if total_bits is not None:
+            self.total_bits = torch.tensor(list(total_bits), dtype=torch.int32, device=self.device)
+
+    # ------------------------------------------------------------------ steps
+    def _fill(self, logits: Optional[torch.Tensor]) -> N.CodecParams:
+        p = self._p
+        if logits is not None:
+            if logits.dtype != torch.float32 or logits.device.type != "cuda" or logits.dim() != 2 \
+                    or logits.shape[0] != self.B or logits.shape[1] != self.V or logits.stride(1) != 1:
+                raise N.NativeLibraryError("logits must be a float32 CUDA tensor [B, V] with unit inner stride")
+            p.logits = logits.data_ptr(); p.ld = logits.stride(0)
+        else:
+            p.logits = None; p.ld = self.V
+        p.B = self.B; p.V = self.V; p.temp = self.temp; p.param = self.param; p.topk = self.topk
+        p.mask_id[0], p.mask_id[1] = self.mask_ids[0], self.mask_ids[1]
+        p.phase = self.phase.data_ptr(); p.status = self.status.data_ptr()
+        p.ntok = self.ntok.data_ptr(); p.token_cap = self.token_cap; p.ntok_total = N.ptr(self.ntok_total)
+        p.nbits_out = self.nbits.data_ptr(); p.lut = N.ptr(self.lut)
+        return p
+
+    def _check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            self.lib.ns_codec_last_error_string.restype = C.c_char_p
+            msg = self.lib.ns_codec_last_error_string()
+            raise N.NativeLibraryError("%s failed with code %d: %s" % (what, rc, (msg or b"").decode()))
+
+    def encode_step(self, logits: torch.Tensor) -> None:
+        p = self._fill(logits)
+        p.msg = self.msg.data_ptr(); p.msg_stride = self.msg.stride(0); p.msg_len = self.msg_len.data_ptr()
+        p.cursor = self.cursor.data_ptr()
+        p.token_out = self.tokens.data_ptr(); p.token_stride = self.tokens.stride(0)
+        self._check(self._enc(C.byref(p), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "encode step")
+
+    def decode_step(self, logits: Optional[torch.Tensor]) -> None:
+        p = self._fill(logits)
+        p.token_in = self.tokens.data_ptr(); p.token_stride = self.tokens.stride(0)
+        p.out_bits = self.out_bits.data_ptr(); p.out_stride = self.out_bits.stride(0); p.out_len = self.out_len.data_ptr()
+        p.total_bits = N.ptr(self.total_bits)
+        self._check(self._dec(C.byref(p), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "decode step")
+
+    # ------------------------------------------------------------------ loops / results
+    def all_done(self) -> bool:
+        return bool((self.phase == N.PHASE_DONE).all().item())
+
+    def encode(self, logits_fn: Callable[[int], torch.Tensor], *, max_steps: Optional[int] = None,
+               poll_every: int = 16) -> List[List[int]]:
+        for t in range(max_steps if max_steps is not None else self.token_cap):
+            self.encode_step(logits_fn(t))
+            if (t + 1) % poll_every == 0 and self.all_done():
+                break
+        return self.token_lists()
+
+    def decode(self, logits_fn: Callable[[int], torch.Tensor]) -> List[List[int]]:
+        for t in range(int(self.ntok_total.max().item()) if self.B else 0):
+            self.decode_step(logits_fn(t))
+        return self.bit_lists()
+
+    def token_lists(self) -> List[List[int]]:
+        n = self.ntok.cpu().numpy(); tk = self.tokens.cpu().numpy()
+        return [tk[r, : int(n[r])].tolist() for r in range(self.B)]
+
+    def bit_lists(self) -> List[List[int]]:
+        return unpack_bits(self.out_bits.cpu().numpy().view(np.uint32), self.out_len.cpu().numpy())

@@ -1,0 +1,468 @@
+// ns_codecs.cu -- the reference's comparison codecs, one CTA per stream, sm_100a.
+//   rank    src/neuralstego/codec/arithmetic.py:122-231, :370-385   (what load_lm("gpt2-fa") runs)
+//   huffman code_base/huffman_baseline.py:7-71, :73-165 ; code_base/huffman.py:12-76
+//   bins    code_base/block_baseline.py:26-97, :99-189
+// The row is staged in shared memory once (rank, Huffman) or streamed (bins).  Order everywhere:
+// larger logit first, equal logits by lower token id.
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "ns_block.cuh"
+
+namespace {
+
+constexpr int CODEC_LIST_CAP = LIST_CAP;     // 512 gathered elements (Huffman: 2^bits_per_word <= 512)
+constexpr int HUF_MAX_LEAVES = 512;
+
+enum { K_RANK_ENC = 0, K_RANK_DEC, K_HUF_ENC, K_HUF_DEC, K_BINS_ENC, K_BINS_DEC };
+
+struct HufNode { float freq; int left, right, parent; };   // leaves: index < n, left = right = -1
+
+struct CodecShared {
+  unsigned char* raw;
+  uint32_t* hist;
+  ListEntry* list;
+  Scalars* sc;
+  float* keys;
+};
+
+__device__ __forceinline__ CodecShared carve(unsigned char* smem_raw) {
+  CodecShared s;
+  s.raw = smem_raw;
+  s.hist = reinterpret_cast<uint32_t*>(smem_raw + NS_EXP_N * 8);
+  s.list = reinterpret_cast<ListEntry*>(smem_raw + NS_EXP_N * 8 + HIST_BYTES);
+  s.sc = reinterpret_cast<Scalars*>(smem_raw + NS_EXP_N * 8 + HIST_BYTES + LIST_CAP * sizeof(ListEntry));
+  s.keys = reinterpret_cast<float*>(smem_raw + FIXED_BYTES);
+  return s;
+}
+
+// Stage row `row` of the logits in shared memory (same 16-byte phase as in global memory);
+// -0 is folded into +0; `mask_value` is written to the forbidden tokens.  Returns the row pointer.
+__device__ float* stage_row(const ns_codec_params& P, int row, CodecShared& sm, bool use_mask) {
+  constexpr int NB = HIST_BYTES / 4;
+  const int tid = threadIdx.x;
+  const int V = P.V;
+  const float* g = P.logits + (size_t)row * (size_t)P.ld;
+  const int mis = (int)(((uintptr_t)g & 15u) >> 2);
+  float* keys = sm.keys + mis;
+  int head = (4 - mis) & 3;
+  if (head > V) head = V;
+  if (tid < head) keys[tid] = g[tid] + 0.0f;
+  const int nvec = (V - head) >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(g + head);
+  float4* s4 = reinterpret_cast<float4*>(keys + head);
+  for (int i = tid; i < nvec; i += NT) {
+    float4 v = __ldg(g4 + i);
+    v.x += 0.0f; v.y += 0.0f; v.z += 0.0f; v.w += 0.0f;
+    s4[i] = v;
+  }
+  const int done = head + (nvec << 2);
+  if (tid < V - done) keys[done + tid] = g[done + tid] + 0.0f;
+  for (int i = tid; i < NB; i += NT) sm.hist[i] = 0;
+  if (tid == 0) sm.sc->list_count = 0;
+  __syncthreads();
+  if (use_mask && tid < 2) {
+    const int id = P.mask_id[tid];
+    if (id >= 0 && id < V) keys[id] = -1e10f;                // huffman_baseline.py:26-27, block_baseline.py:46-47
+  }
+  __syncthreads();
+  return keys;
+}
+
+// The element whose 0-based position in the coder's order is `pos`, by a count histogram over
+// 2048 monotone key buckets + exact resolution inside the bucket.  Returns -1 if pos is out of range.
+__device__ int element_at(const float* keys, int V, u64 pmax, u64 pmin, u64 pos, CodecShared& sm,
+                          int32_t* status) {
+  constexpr int NB = HIST_BYTES / 4;
+  const int tid = threadIdx.x;
+  const float m = key_of_pack(pmax);
+  const float span = m - key_of_pack(pmin);
+  const float scale = span > 0.0f ? (float)NB / span : 0.0f;
+  __syncthreads();
+  for (int i = tid; i < NB; i += NT) sm.hist[i] = 0;
+  if (tid == 0) sm.sc->list_count = 0;
+  __syncthreads();
+  for (int i = tid; i < V; i += NT) atomicAdd(&sm.hist[bin_of(keys[i], m, scale, NB)], 1u);
+  __syncthreads();
+  sel_locate<uint32_t, NB>(sm.hist, pos, sm.sc);
+  const int tb = sm.sc->sel_bin;
+  const u64 prefix = sm.sc->sel_prefix;
+  if (tb < 0) return -1;
+  for (int i = tid; i < V; i += NT) {
+    const float k = keys[i];
+    if (bin_of(k, m, scale, NB) == tb) {
+      const int slot = atomicAdd(&sm.sc->list_count, 1);
+      if (slot < CODEC_LIST_CAP) { sm.list[slot].pack = pack_of(k, i); sm.list[slot].w = 1; }
+    }
+  }
+  __syncthreads();
+  int n = sm.sc->list_count;
+  if (n > CODEC_LIST_CAP) { n = CODEC_LIST_CAP; if (tid == 0 && status) atomicOr(status, NS_ST_BIN_OVERFLOW); }
+  sel_resolve(sm.list, n, pos, prefix, sm.sc);
+  const int found = sm.sc->res_found ? sm.sc->res_idx : -1;
+  __syncthreads();
+  return found;
+}
+
+__device__ __forceinline__ bool stream_live(const ns_codec_params& P, int row, bool decode, int* slot_out) {
+  const uint8_t phase = P.phase ? P.phase[row] : (uint8_t)NS_PHASE_CODING;
+  const int slot = P.ntok ? P.ntok[row] : 0;
+  *slot_out = slot;
+  if (phase == NS_PHASE_DONE) return false;
+  if (!decode && P.ntok && slot >= P.token_cap) {
+    if (threadIdx.x == 0) {
+      if (P.phase) P.phase[row] = NS_PHASE_DONE;
+      if (P.status) atomicOr(&P.status[row], NS_ST_TOKEN_OVERFLOW);
+    }
+    return false;
+  }
+  if (decode && P.ntok_total && slot >= P.ntok_total[row]) {
+    if (threadIdx.x == 0 && P.phase) P.phase[row] = NS_PHASE_DONE;
+    return false;
+  }
+  return true;
+}
+
+__device__ __forceinline__ void emit_token(const ns_codec_params& P, int row, int slot, int token, int consumed) {
+  const int nc = P.cursor[row] + consumed;
+  P.cursor[row] = nc;
+  P.token_out[(size_t)row * P.token_stride + slot] = token;
+  if (P.ntok) P.ntok[row] = slot + 1;
+  if (P.nbits_out) P.nbits_out[row] = (uint8_t)consumed;
+  if (P.phase && nc >= P.msg_len[row]) P.phase[row] = NS_PHASE_DONE;
+}
+
+__device__ __forceinline__ void emit_bits(const ns_codec_params& P, int row, int slot, u64 value, int count) {
+  const int olen = P.out_len[row];
+  if (count > 0) ns_write_bits(P.out_bits + (size_t)row * P.out_stride, olen, value, count);
+  P.out_len[row] = olen + count;
+  if (P.ntok) P.ntok[row] = slot + 1;
+  if (P.nbits_out) P.nbits_out[row] = (uint8_t)count;
+  if (P.phase && P.ntok_total && slot + 1 >= P.ntok_total[row]) P.phase[row] = NS_PHASE_DONE;
+}
+
+// max / min of the row as packs (key, lowest id)
+__device__ void row_extent(const float* keys, int V, Scalars* sc, u64* pmax, u64* pmin) {
+  u64 a = 0, b = ~0ull;
+  for (int i = threadIdx.x; i < V; i += NT) {
+    const u64 p = pack_of(keys[i], i);
+    a = p > a ? p : a;
+    b = p < b ? p : b;
+  }
+  *pmax = block_reduce_u(a, OpMaxU(), sc->red);
+  *pmin = block_reduce_u(b, OpMinU(), sc->red);
+}
+
+// ------------------------------------------------------------------------------------------
+// (B) rank codec
+// ------------------------------------------------------------------------------------------
+template <bool DECODE>
+__global__ void __launch_bounds__(NT, 1) rank_kernel(ns_codec_params P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CodecShared sm = carve(smem_raw);
+  const int row = blockIdx.x, tid = threadIdx.x, V = P.V;
+  int slot;
+  if (!stream_live(P, row, DECODE, &slot)) return;
+  const float* keys = stage_row(P, row, sm, false);
+  u64 pmax, pmin;
+  row_extent(keys, V, sm.sc, &pmax, &pmin);
+  const float m = key_of_pack(pmax);
+  // tokens with p > 0 (codec/arithmetic.py:372): fp64 softmax underflows below exp(-745)
+  const double dm = (double)m / P.temp;
+  u64 cnt = 0;
+  for (int i = tid; i < V; i += NT) cnt += (((double)keys[i] / P.temp - dm) >= -745.0) ? 1 : 0;
+  u64 n_pos = block_reduce_u(cnt, OpAddU(), sm.sc->red);
+  if (P.topk > 0 && n_pos > (u64)P.topk) n_pos = (u64)P.topk;          // quality.py:76-81
+  int capacity = 0;
+  while ((2ull << capacity) <= n_pos) ++capacity;                       // floor(log2(n_pos)), :379
+  if (capacity <= 0) {                                                  // ArithmeticRangeError :149
+    if (tid == 0 && P.status) atomicOr(&P.status[row], NS_ST_OUT_OF_RANGE);
+    if (tid == 0 && P.phase) P.phase[row] = NS_PHASE_DONE;
+    return;
+  }
+  if (!DECODE) {
+    const int cursor = P.cursor[row], mlen = P.msg_len[row];
+    const u64 index = ns_read_bits(P.msg + (size_t)row * P.msg_stride, cursor, mlen, capacity);   // :153-157
+    int token = element_at(keys, V, pmax, pmin, index, sm, P.status ? &P.status[row] : nullptr);
+    if (token < 0) token = id_of_pack(pmax);
+    int consumed = mlen - cursor;
+    if (consumed > capacity) consumed = capacity;                       // :155
+    if (tid == 0) emit_token(P, row, slot, token, consumed);
+  } else {
+    int tok = P.token_in[(size_t)row * P.token_stride + slot];
+    if (tok < 0 || tok >= V) tok = id_of_pack(pmax);
+    const u64 tp = pack_of(keys[tok], tok);
+    u64 before = 0;
+    for (int i = tid; i < V; i += NT) before += pack_of(keys[i], i) > tp ? 1 : 0;
+    const u64 rank = block_reduce_u(before, OpAddU(), sm.sc->red);      // ranked_tokens.index(token), :211
+    if (tid == 0) {
+      if (rank >= (1ull << capacity) && P.status) atomicOr(&P.status[row], NS_ST_OUT_OF_RANGE);   // :212-213
+      const int total = P.total_bits ? P.total_bits[row] : 0x7fffffff;
+      int take = total - P.out_len[row];
+      if (take > capacity) take = capacity;
+      if (take < 0) take = 0;
+      emit_bits(P, row, slot, (rank & ((1ull << capacity) - 1ull)) >> (capacity - take), take);   // :215-216
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Huffman baseline
+// ------------------------------------------------------------------------------------------
+// CPython heapq on node indices ordered by freq only (huffman.py:21-22): exact replica of
+// heappush/_siftdown and heappop/_siftup so that ties resolve as in the reference.
+__device__ __forceinline__ bool huf_lt(const HufNode* nd, int a, int b) { return nd[a].freq < nd[b].freq; }
+__device__ void huf_siftdown(int* heap, const HufNode* nd, int startpos, int pos) {
+  const int newitem = heap[pos];
+  while (pos > startpos) {
+    const int parentpos = (pos - 1) >> 1;
+    const int parent = heap[parentpos];
+    if (huf_lt(nd, newitem, parent)) { heap[pos] = parent; pos = parentpos; continue; }
+    break;
+  }
+  heap[pos] = newitem;
+}
+__device__ void huf_siftup(int* heap, const HufNode* nd, int len, int pos) {
+  const int startpos = pos;
+  const int newitem = heap[pos];
+  int childpos = 2 * pos + 1;
+  while (childpos < len) {
+    const int rightpos = childpos + 1;
+    if (rightpos < len && !huf_lt(nd, heap[childpos], heap[rightpos])) childpos = rightpos;
+    heap[pos] = heap[childpos];
+    pos = childpos;
+    childpos = 2 * pos + 1;
+  }
+  heap[pos] = newitem;
+  huf_siftdown(heap, nd, startpos, pos);
+}
+__device__ int huf_pop(int* heap, const HufNode* nd, int* len) {
+  const int last = heap[--(*len)];
+  if (*len > 0) {
+    const int ret = heap[0];
+    heap[0] = last;
+    huf_siftup(heap, nd, *len, 0);
+    return ret;
+  }
+  return last;
+}
+
+template <bool DECODE>
+__global__ void __launch_bounds__(NT, 1) huffman_kernel(ns_codec_params P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CodecShared sm = carve(smem_raw);
+  const int row = blockIdx.x, tid = threadIdx.x, V = P.V;
+  int slot;
+  if (!stream_live(P, row, DECODE, &slot)) return;
+  const float* keys = stage_row(P, row, sm, true);
+  u64 pmax, pmin;
+  row_extent(keys, V, sm.sc, &pmax, &pmin);
+  const float m = key_of_pack(pmax);
+  int n = 1 << P.param;                                      // top 2^bits_per_word options, :30
+  if (n > V) n = V;
+  // log_softmax over the whole row (:32), accumulated in double like torch's CPU kernel
+  double acc = 0.0;
+  for (int i = tid; i < V; i += NT) acc += (double)expf(keys[i] - m);
+  __syncthreads();
+  const double sum = block_sum_d(acc, sm.sc->red);
+  const float lse = (float)log(sum);
+  // the n-th element of the order bounds the kept set
+  const int bound_id = element_at(keys, V, pmax, pmin, (u64)(n - 1), sm, P.status ? &P.status[row] : nullptr);
+  const u64 bound = bound_id >= 0 ? pack_of(keys[bound_id], bound_id) : pmin;
+  __syncthreads();
+  if (tid == 0) sm.sc->list_count = 0;
+  __syncthreads();
+  for (int i = tid; i < V; i += NT) {
+    const u64 p = pack_of(keys[i], i);
+    if (p >= bound) {
+      const int s = atomicAdd(&sm.sc->list_count, 1);
+      if (s < CODEC_LIST_CAP) { sm.list[s].pack = p; sm.list[s].w = 0; }
+    }
+  }
+  __syncthreads();
+  // order the n survivors: w := rank
+  for (int c = tid; c < n; c += NT) {
+    const u64 pc = sm.list[c].pack;
+    int r = 0;
+    for (int o = 0; o < n; ++o) r += sm.list[o].pack > pc ? 1 : 0;
+    sm.list[c].w = (u64)r;
+  }
+  __syncthreads();
+  // scratch carved from the histogram area (8 KB): ids by rank, nodes, heap
+  int* ids = reinterpret_cast<int*>(sm.hist);                          // [n]
+  int* heap = ids + HUF_MAX_LEAVES;                                    // [n]
+  HufNode* nd = reinterpret_cast<HufNode*>(sm.raw);                    // [2n-1] in the (unused) exp-table + start of hist? no: table area only
+  // table area is 4 KB = 256 nodes; larger trees continue in the key row's tail padding -> keep n <= 128 in the table,
+  // otherwise place nodes after the list (list holds n <= 512 entries of 16 B = 8 KB, nodes need 16 KB): use global-free fallback
+  if (n > 128) nd = reinterpret_cast<HufNode*>(sm.keys + ((V + 8 + 3) & ~3));   // beyond the row (capacity checked on host)
+  for (int c = tid; c < n; c += NT) {
+    const int r = (int)sm.list[c].w;
+    const u64 pc = sm.list[c].pack;
+    ids[r] = id_of_pack(pc);
+    nd[r].freq = expf((key_of_pack(pc) - m) - lse);                     // probs = exp(log_probs), :33
+    nd[r].left = -1; nd[r].right = -1; nd[r].parent = -1;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int len = 0;
+    for (int i = 0; i < n; ++i) { heap[len] = i; ++len; huf_siftdown(heap, nd, 0, len - 1); }   // make_heap_from_array
+    int next = n;
+    while (len > 1) {                                                  // merge_nodes, huffman.py:48-57
+      const int n1 = huf_pop(heap, nd, &len);
+      const int n2 = huf_pop(heap, nd, &len);
+      nd[next].freq = nd[n1].freq + nd[n2].freq;
+      nd[next].left = n1; nd[next].right = n2; nd[next].parent = -1;
+      nd[n1].parent = next; nd[n2].parent = next;
+      heap[len] = next; ++len; huf_siftdown(heap, nd, 0, len - 1);
+      ++next;
+    }
+    const int root = heap[0];
+    if (!DECODE) {
+      const int cursor = P.cursor[row], mlen = P.msg_len[row];
+      const uint32_t* msg = P.msg + (size_t)row * P.msg_stride;
+      int node = root, i = cursor;
+      while (nd[node].left >= 0) {                                     // :47-52, exhausted message reads as 0
+        const int bit = (i < mlen) ? (int)((msg[i >> 5] >> (31 - (i & 31))) & 1u) : 0;
+        node = bit ? nd[node].right : nd[node].left;
+        ++i;
+      }
+      emit_token(P, row, slot, ids[node], i - cursor);
+    } else {
+      int tok = P.token_in[(size_t)row * P.token_stride + slot];
+      int leaf = -1;
+      for (int r = 0; r < n; ++r) if (ids[r] == tok) leaf = r;
+      if (leaf < 0) { leaf = 0; if (P.status) atomicOr(&P.status[row], NS_ST_OUT_OF_RANGE); }   // :149
+      u64 code = 0;
+      int depth = 0;
+      for (int node = leaf; nd[node].parent >= 0; node = nd[node].parent) {
+        const int par = nd[node].parent;
+        code |= (u64)(nd[par].right == node ? 1 : 0) << depth;          // bits from leaf to root
+        ++depth;
+      }
+      emit_bits(P, row, slot, code, depth);                            // root-to-leaf order = MSB first
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// bins baseline
+// ------------------------------------------------------------------------------------------
+template <bool DECODE>
+__global__ void __launch_bounds__(NT, 1) bins_kernel(ns_codec_params P) {
+  __shared__ u64 red[NWARPS];
+  const int row = blockIdx.x, tid = threadIdx.x, V = P.V;
+  int slot;
+  if (!stream_live(P, row, DECODE, &slot)) return;
+  const int b = P.param;
+  if (DECODE) {
+    if (tid == 0) {
+      int tok = P.token_in[(size_t)row * P.token_stride + slot];
+      if (tok < 0 || tok >= V) tok = 0;
+      const u64 bin = (u64)P.lut[tok];                                 // words2bin[inp[i]], :122
+      u64 rev = 0;                                                     // int2bits is LSB first, :183
+      for (int j = 0; j < b; ++j) rev |= ((bin >> j) & 1ull) << (b - 1 - j);
+      emit_bits(P, row, slot, rev, b);
+    }
+    return;
+  }
+  const int cursor = P.cursor[row], mlen = P.msg_len[row];
+  const uint32_t* msg = P.msg + (size_t)row * P.msg_stride;
+  int bin = 0;
+  for (int j = 0; j < b; ++j) {                                        // bits2int(message[i:i+b]), :79
+    const int i = cursor + j;
+    if (i < mlen) bin |= (int)((msg[i >> 5] >> (31 - (i & 31))) & 1u) << j;
+  }
+  const float* g = P.logits + (size_t)row * (size_t)P.ld;
+  u64 best = 0;
+  for (int i = tid; i < V; i += NT) {
+    if (P.lut[i] == bin) {
+      float k = g[i] + 0.0f;
+      if (i == P.mask_id[0] || i == P.mask_id[1]) k = -1e10f;           // :46-47
+      const u64 p = pack_of(k, i);
+      best = p > best ? p : best;
+    }
+  }
+  best = block_reduce_u(best, OpMaxU(), red);                          // indices[0] of the bin, :80-81
+  if (tid == 0) emit_token(P, row, slot, id_of_pack(best), b);         // i += block_size, :85
+}
+
+thread_local char g_cerr[256] = "";
+int cerr(int code, const char* msg) { snprintf(g_cerr, sizeof(g_cerr), "%s", msg); return code; }
+
+int validate_codec(const ns_codec_params* p, int kind) {
+  if (!p) return cerr(NS_E_NULL, "params is NULL");
+  const bool decode = (kind == K_RANK_DEC || kind == K_HUF_DEC || kind == K_BINS_DEC);
+  const bool needs_logits = kind != K_BINS_DEC;
+  if (needs_logits && !p->logits) return cerr(NS_E_NULL, "logits is NULL");
+  if (p->B < 0 || p->V < 4) return cerr(NS_E_RANGE, "B < 0 or V < 4");
+  if (needs_logits && p->ld < p->V) return cerr(NS_E_RANGE, "ld < V");
+  if ((kind == K_RANK_ENC || kind == K_RANK_DEC || kind == K_HUF_ENC || kind == K_HUF_DEC) && p->V > MAX_VOCAB)
+    return cerr(NS_E_VOCAB, "V exceeds the shared-memory row capacity");
+  if (kind == K_RANK_ENC || kind == K_RANK_DEC) { if (!(p->temp > 0.0)) return cerr(NS_E_RANGE, "temp must be > 0"); }
+  if (kind == K_HUF_ENC || kind == K_HUF_DEC) { if (p->param < 1 || p->param > 9) return cerr(NS_E_RANGE, "bits_per_word must be in [1, 9]"); }
+  if (kind == K_BINS_ENC || kind == K_BINS_DEC) {
+    if (p->param < 1 || p->param > 16) return cerr(NS_E_RANGE, "block_size must be in [1, 16]");
+    if (!p->lut) return cerr(NS_E_NULL, "bins need the word->bin table");
+  }
+  if (!decode) { if (!p->msg || !p->msg_len || !p->cursor || !p->token_out) return cerr(NS_E_NULL, "encode needs msg/msg_len/cursor/token_out"); }
+  else { if (!p->token_in || !p->out_bits || !p->out_len) return cerr(NS_E_NULL, "decode needs token_in/out_bits/out_len"); }
+  return NS_OK;
+}
+
+template <typename K>
+int launch_codec(K kernel, const ns_codec_params* p, int smem, bool* configured, void* stream) {
+  if (!*configured && smem > 0) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e != cudaSuccess) { cerr((int)e, cudaGetErrorString(e)); return e == cudaErrorInvalidDeviceFunction ? NS_E_NODEVICE : (int)e; }
+    *configured = true;
+  }
+  if (p->B == 0) return NS_OK;
+  kernel<<<p->B, NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cerr((int)e, cudaGetErrorString(e));
+  return NS_OK;
+}
+
+int row_smem(const ns_codec_params* p, bool huffman) {
+  int bytes = FIXED_BYTES + (p->V + 8) * 4;
+  if (huffman) bytes += 2 * HUF_MAX_LEAVES * (int)sizeof(HufNode) + 64;   // node pool behind the row for large trees
+  return bytes;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ns_sizeof_codec_params(void) { return (int)sizeof(ns_codec_params); }
+const char* ns_codec_last_error_string(void) { return g_cerr; }
+
+int ns_rank_encode_step(const ns_codec_params* p, void* s) {
+  int rc = validate_codec(p, K_RANK_ENC); if (rc) return rc;
+  static bool c = false; return launch_codec(rank_kernel<false>, p, row_smem(p, false), &c, s);
+}
+int ns_rank_decode_step(const ns_codec_params* p, void* s) {
+  int rc = validate_codec(p, K_RANK_DEC); if (rc) return rc;
+  static bool c = false; return launch_codec(rank_kernel<true>, p, row_smem(p, false), &c, s);
+}
+int ns_huffman_encode_step(const ns_codec_params* p, void* s) {
+  int rc = validate_codec(p, K_HUF_ENC); if (rc) return rc;
+  if (row_smem(p, true) > SMEM_LIMIT && p->param > 7) return cerr(NS_E_VOCAB, "bits_per_word > 7 needs a smaller vocabulary");
+  static bool c = false; return launch_codec(huffman_kernel<false>, p, row_smem(p, p->param > 7), &c, s);
+}
+int ns_huffman_decode_step(const ns_codec_params* p, void* s) {
+  int rc = validate_codec(p, K_HUF_DEC); if (rc) return rc;
+  if (row_smem(p, true) > SMEM_LIMIT && p->param > 7) return cerr(NS_E_VOCAB, "bits_per_word > 7 needs a smaller vocabulary");
+  static bool c = false; return launch_codec(huffman_kernel<true>, p, row_smem(p, p->param > 7), &c, s);
+}
+int ns_bins_encode_step(const ns_codec_params* p, void* s) {
+  int rc = validate_codec(p, K_BINS_ENC); if (rc) return rc;
+  static bool c = false; return launch_codec(bins_kernel<false>, p, 0, &c, s);
+}
+int ns_bins_decode_step(const ns_codec_params* p, void* s) {
+  int rc = validate_codec(p, K_BINS_DEC); if (rc) return rc;
+  static bool c = false; return launch_codec(bins_kernel<true>, p, 0, &c, s);
+}
+
+}  // extern "C"
