@@ -143,13 +143,15 @@ __device__ __forceinline__ void emit_bits(const ns_codec_params& P, int row, int
   if (P.phase && P.ntok_total && slot + 1 >= P.ntok_total[row]) P.phase[row] = NS_PHASE_DONE;
 }
 
-// max / min of the row as packs (key, lowest id)
+// max / min of the row as packs (key, lowest id); forbidden tokens (-1e10) and -inf do not stretch
+// the bucket range (they all land in the last bucket)
 __device__ void row_extent(const float* keys, int V, Scalars* sc, u64* pmax, u64* pmin) {
   u64 a = 0, b = ~0ull;
   for (int i = threadIdx.x; i < V; i += NT) {
-    const u64 p = pack_of(keys[i], i);
+    const float k = keys[i];
+    const u64 p = pack_of(k, i);
     a = p > a ? p : a;
-    b = p < b ? p : b;
+    if (k > -1e9f) b = p < b ? p : b;
   }
   *pmax = block_reduce_u(a, OpMaxU(), sc->red);
   *pmin = block_reduce_u(b, OpMinU(), sc->red);
