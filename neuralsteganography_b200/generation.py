@@ -1,0 +1,91 @@
+"""Device-resident generation loop: GPT-2 trunk step + coder step, replayed as one CUDA graph.
+
+Replaces the per-token Python loop of the reference (code_base/arithmetic.py:114-210 encode,
+:255-371 decode), which synchronises with the host about ten times per token.  Here message bits,
+intervals, cursors, token buffers and the KV cache live in HBM; the host replays a captured graph and
+reads one "all done" flag every ``poll_every`` steps.
+"""
+
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from .coder import ArithmeticStreams
+from .trunk import StaticGPT2
+
+
+class StegoGenerator:
+    """B streams sharing one context length, GPT-2 shaped trunk, arithmetic coder (A)."""
+
+    def __init__(self, hf_model, batch: int, *, max_len: int = 256, precision: int = 16, temp: float = 1.0,
+                 topk: int = 50000, finish_sent: bool = False, sent_end: Optional[torch.Tensor] = None,
+                 device="cuda", use_graph: bool = True, trunk_dtype: torch.dtype = torch.float32):
+        self.B = int(batch)
+        self.device = torch.device(device)
+        self.trunk = StaticGPT2(hf_model, batch, max_len=max_len, device=device, dtype=trunk_dtype)
+        self.V = self.trunk.vocab
+        self.max_len = int(max_len)
+        self.kw = dict(precision=precision, temp=temp, topk=topk, finish_sent=finish_sent, sent_end=sent_end)
+        self.use_graph = bool(use_graph)
+        self.logits = torch.zeros(self.B, self.V, dtype=torch.float32, device=self.device)
+        self._rows = torch.arange(self.B, device=self.device)
+        self.steps_run = 0
+
+    # one loop iteration: coder on the current logits, then the trunk on the token just fixed
+    def _iter(self, coder: ArithmeticStreams, decode: bool) -> None:
+        if decode:
+            coder.decode_step(self.logits)
+        else:
+            coder.encode_step(self.logits)
+        last = (coder.ntok.long() - 1).clamp(min=0)
+        prev = coder.tokens[self._rows, last].long().clamp(min=0)      # finished streams feed a stale token
+        self.logits.copy_(self.trunk.step(prev))
+
+    def _run(self, coder: ArithmeticStreams, decode: bool, max_steps: int, poll_every: int) -> None:
+        graph = None
+        t = 0
+        while t < max_steps:
+            if self.use_graph and graph is None and t >= 2:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._iter(coder, decode)
+                # capture does not execute: this step still has to run
+            if graph is not None:
+                graph.replay()
+            else:
+                self._iter(coder, decode)
+            t += 1
+            if t % poll_every == 0 and coder.all_done():
+                break
+        self.steps_run = t
+
+    def _prefill(self, contexts: torch.Tensor) -> None:
+        contexts = contexts.to(self.device)
+        if contexts.dim() == 1:
+            contexts = contexts[None].expand(self.B, -1)
+        contexts = contexts[:, -1022:]                                  # arithmetic.py:90
+        self.trunk.reset()
+        self.logits.copy_(self.trunk.prefill(contexts.contiguous()))
+
+    def encode(self, contexts: torch.Tensor, messages: Sequence[Sequence[int]], *, poll_every: int = 16) -> List[List[int]]:
+        """Cover tokens for one message (list of 0/1) per stream."""
+        room = self.max_len - int(contexts.shape[-1]) - 1
+        coder = ArithmeticStreams(self.B, self.V, device=self.device, token_cap=max(1, room), **self.kw)
+        coder.set_messages(messages)
+        self._prefill(contexts)
+        self._run(coder, False, room, poll_every)
+        self.coder = coder
+        return coder.token_lists()
+
+    def decode(self, contexts: torch.Tensor, token_lists: Sequence[Sequence[int]], *, poll_every: int = 16) -> List[List[int]]:
+        """Recovered bits (message + trailing bits, as the reference returns them) per stream."""
+        n = max((len(t) for t in token_lists), default=0)
+        kw = dict(self.kw); kw["finish_sent"] = False
+        coder = ArithmeticStreams(self.B, self.V, device=self.device, token_cap=max(1, n), **kw)
+        coder.set_tokens(token_lists)
+        self._prefill(contexts)
+        self._run(coder, True, n, poll_every)
+        self.coder = coder
+        return coder.bit_lists()

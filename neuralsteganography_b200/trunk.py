@@ -1,0 +1,114 @@
+"""GPT-2 trunk with a static KV cache: the LM side of the device-resident generation loop.
+
+The reference drives HuggingFace ``GPT2LMHeadModel`` one token at a time and converts its
+cache object every step (code_base/arithmetic.py:115-122, utils.py:19-30).  Here the same
+weights run through plain PyTorch ops over pre-allocated KV buffers so that one decoding
+step has fixed shapes and no host decisions -- it can be captured in a CUDA graph together
+with the coder step.  PyTorch is plumbing here (GEMMs via cuBLAS); the product is the coder.
+
+Position rule of the reference: the first call sees the whole context at positions
+0..L-1, later calls use ``past_len % n_positions`` (arithmetic.py:44-48); the context is
+cut to its last 1022 tokens (:90).  Streams longer than ``n_positions - 2`` would need the
+reference's sliding window (utils.py:19-30), which this trunk does not implement.
+"""
+
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+
+class StaticGPT2:
+    """Inference-only GPT-2 (gelu_new, pre-LN) over static KV buffers ``[layers, B, heads, T, hd]``."""
+
+    def __init__(self, hf_model, batch: int, max_len: Optional[int] = None, device="cuda",
+                 dtype: torch.dtype = torch.float32):
+        cfg = hf_model.config
+        self.n_layer, self.n_head, self.n_embd = cfg.n_layer, cfg.n_head, cfg.n_embd
+        self.n_positions, self.vocab = cfg.n_positions, cfg.vocab_size
+        self.eps = cfg.layer_norm_epsilon
+        self.hd = self.n_embd // self.n_head
+        self.B = int(batch)
+        self.T = int(max_len or cfg.n_positions)
+        self.device, self.dtype = torch.device(device), dtype
+        sd = {k: v.detach().to(self.device, dtype) for k, v in hf_model.state_dict().items()}
+        g = lambda name: sd[name].contiguous()
+        self.wte, self.wpe = g("transformer.wte.weight"), g("transformer.wpe.weight")
+        self.layers = []
+        for i in range(self.n_layer):
+            p = "transformer.h.%d." % i
+            self.layers.append(dict(
+                ln1w=g(p + "ln_1.weight"), ln1b=g(p + "ln_1.bias"),
+                qkvw=g(p + "attn.c_attn.weight"), qkvb=g(p + "attn.c_attn.bias"),       # Conv1D: x @ W + b
+                pw=g(p + "attn.c_proj.weight"), pb=g(p + "attn.c_proj.bias"),
+                ln2w=g(p + "ln_2.weight"), ln2b=g(p + "ln_2.bias"),
+                fcw=g(p + "mlp.c_fc.weight"), fcb=g(p + "mlp.c_fc.bias"),
+                ow=g(p + "mlp.c_proj.weight"), ob=g(p + "mlp.c_proj.bias")))
+        self.lnfw, self.lnfb = g("transformer.ln_f.weight"), g("transformer.ln_f.bias")
+        self.lm_head = g("lm_head.weight") if "lm_head.weight" in sd else self.wte   # tied
+        self.k = torch.zeros(self.n_layer, self.B, self.n_head, self.T, self.hd, device=self.device, dtype=dtype)
+        self.v = torch.zeros_like(self.k)
+        self.length = torch.zeros((), dtype=torch.long, device=self.device)   # tokens in the cache (same for all streams)
+        self._arange_t = torch.arange(self.T, device=self.device)
+
+    # ------------------------------------------------------------------ context (variable length, eager)
+    @torch.no_grad()
+    def prefill(self, context: torch.Tensor) -> torch.Tensor:
+        """Run ``context`` [B, L] (L <= T - 1) through the trunk; returns fp32 logits [B, V] of its last token."""
+        B, L = context.shape
+        assert B == self.B and L < self.T
+        pos = torch.arange(L, device=self.device)
+        x = self.wte[context] + self.wpe[pos][None]
+        mask = torch.ones(L, L, device=self.device, dtype=torch.bool).tril()
+        for i, w in enumerate(self.layers):
+            h = F.layer_norm(x, (self.n_embd,), w["ln1w"], w["ln1b"], self.eps)
+            qkv = h @ w["qkvw"] + w["qkvb"]
+            q, k, v = qkv.split(self.n_embd, dim=-1)
+            q = q.view(B, L, self.n_head, self.hd).transpose(1, 2)
+            k = k.view(B, L, self.n_head, self.hd).transpose(1, 2)
+            v = v.view(B, L, self.n_head, self.hd).transpose(1, 2)
+            self.k[i, :, :, :L] = k
+            self.v[i, :, :, :L] = v
+            att = (q @ k.transpose(-1, -2)) / math.sqrt(self.hd)
+            att = att.masked_fill(~mask, torch.finfo(att.dtype).min).softmax(-1)
+            a = (att @ v).transpose(1, 2).reshape(B, L, self.n_embd)
+            x = x + (a @ w["pw"] + w["pb"])
+            h = F.layer_norm(x, (self.n_embd,), w["ln2w"], w["ln2b"], self.eps)
+            x = x + (F.gelu(h @ w["fcw"] + w["fcb"], approximate="tanh") @ w["ow"] + w["ob"])
+        self.length.fill_(L)
+        x = F.layer_norm(x[:, -1], (self.n_embd,), self.lnfw, self.lnfb, self.eps)
+        return (x @ self.lm_head.t()).float().contiguous()
+
+    # ------------------------------------------------------------------ one token (fixed shapes, graph-capturable)
+    @torch.no_grad()
+    def step(self, tokens: torch.Tensor) -> torch.Tensor:
+        """Append ``tokens`` [B] (int64) at position ``length``; returns fp32 logits [B, V].  No host sync."""
+        B = self.B
+        pos = self.length.remainder(self.n_positions)                                # arithmetic.py:44-48
+        x = self.wte[tokens] + self.wpe[pos][None]
+        slot = self.length.clamp(max=self.T - 1).view(1)                             # device index: no host sync
+        live = (self._arange_t <= self.length)[None, None, None, :]                  # keys 0..length
+        for i, w in enumerate(self.layers):
+            h = F.layer_norm(x, (self.n_embd,), w["ln1w"], w["ln1b"], self.eps)
+            qkv = h @ w["qkvw"] + w["qkvb"]
+            q, k, v = qkv.split(self.n_embd, dim=-1)
+            q = q.view(B, self.n_head, 1, self.hd)
+            k = k.view(B, self.n_head, 1, self.hd)
+            v = v.view(B, self.n_head, 1, self.hd)
+            self.k[i].index_copy_(2, slot, k)                                        # cache row `length`
+            self.v[i].index_copy_(2, slot, v)
+            att = (q @ self.k[i].transpose(-1, -2)) / math.sqrt(self.hd)             # [B, H, 1, T]
+            att = att.masked_fill(~live, torch.finfo(att.dtype).min).softmax(-1)
+            a = (att @ self.v[i]).reshape(B, self.n_embd)
+            x = x + (a @ w["pw"] + w["pb"])
+            h = F.layer_norm(x, (self.n_embd,), w["ln2w"], w["ln2b"], self.eps)
+            x = x + (F.gelu(h @ w["fcw"] + w["fcb"], approximate="tanh") @ w["ow"] + w["ob"])
+        self.length.add_(1)
+        x = F.layer_norm(x, (self.n_embd,), self.lnfw, self.lnfb, self.eps)
+        return (x @ self.lm_head.t()).float().contiguous()
+
+    def reset(self) -> None:
+        self.length.zero_()
