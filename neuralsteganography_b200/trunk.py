@@ -87,8 +87,8 @@ class StaticGPT2:
     def step(self, tokens: torch.Tensor) -> torch.Tensor:
         """Append ``tokens`` [B] (int64) at position ``length``; returns fp32 logits [B, V].  No host sync."""
         B = self.B
-        pos = self.length.remainder(self.n_positions)                                # arithmetic.py:44-48
-        x = self.wte[tokens] + self.wpe[pos][None]
+        pos = self.length.remainder(self.n_positions).view(1)                        # arithmetic.py:44-48
+        x = self.wte.index_select(0, tokens) + self.wpe.index_select(0, pos)         # tensor indices: no host sync
         slot = self.length.clamp(max=self.T - 1).view(1)                             # device index: no host sync
         live = (self._arange_t <= self.length)[None, None, None, :]                  # keys 0..length
         for i, w in enumerate(self.layers):
