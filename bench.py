@@ -275,13 +275,15 @@ def run_gpu_arm(args):
     # final gather of the cover tokens (the only collective; outside the hot path)
     gather_ms = None
     if world > 1:
+        from neuralsteganography_b200.sharding import gather_ragged
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        out = [torch.empty_like(st.tokens) for _ in range(world)] if rank == 0 else None
         g0.record()
-        dist.gather(st.tokens, out, dst=0)
+        gathered = gather_ragged(st.tokens, st.ntok, dst=0)
         g1.record()
         torch.cuda.synchronize()
         gather_ms = g0.elapsed_time(g1)
+        if rank == 0:
+            assert len(gathered) == world * B
         t_all = torch.tensor([ms, dms, ems], device=dev, dtype=torch.float64)
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
         ms, dms, ems = [float(x) for x in t_all.tolist()]
@@ -308,13 +310,13 @@ def run_gpu_arm(args):
             "decode_tokens_per_sec": tokens / (dms * 1e-3),
             "live_streams_at_end": live, "roundtrip_ok": bool(rt_ok),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "ac_step_kernel<ENC>",
+                         "traffic": None, "peak_source": peak_src, "kernel": "ac_fast_kernel<unit_temp, ENC>",
                          "algorithmic_bytes_per_token": ALGO_BYTES_PER_TOKEN},
             "cpu_baseline": cpu,
             "e2e": {"value": world * B * e2e_steps / (ems * 1e-3), "unit": "tokens/s",
                     "h2d_bytes_per_step": B * V * 4, "d2h_bytes_per_step": B * 4,
                     "note": "host logits (pinned) -> H2D -> ns_ac_encode_step -> tokens D2H, per rank"},
-            "gpu_launches": K,
+            "gpu_launches": 2 * K,   # per step: ac_fast_kernel + ac_step_kernel draining the hand-over queue
             "gather_ms": gather_ms,
             "clocks": clocks,
         }
