@@ -13,7 +13,7 @@ import os
 from typing import Optional
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libns_coder.so")
+LIB_PATH = os.environ.get("NS_CODER_LIB") or os.path.join(_PKG_DIR, "libns_coder.so")   # override: kernel experiments
 
 NS_OK = 0
 PHASE_CODING, PHASE_TAIL, PHASE_DONE = 0, 1, 2

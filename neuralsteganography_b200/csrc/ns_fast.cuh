@@ -7,7 +7,7 @@
 //       sum of exp) runs over the pieces already there.  The CTA's next row is prefetched into L2.
 //   P1  ONE fp64 exp per element (10 fp64 ops): exact sum of all e_i in a fixed order, exact sum of
 //       the provisionally-cut ones, elements within 2^-10 of the provisional cutoff go to a small
-//       list with their exact e ; the word is overwritten in place by trunc_fp32(e_i) (0 if not kept)
+//       list with their exact e ; the word is overwritten in place by the high word of e_i (0 if not kept)
 //   FIX exact normaliser -> the provisional cutoff is verified, list elements classified exactly,
 //       S_kept and C = range / S_kept exact
 //   P2  q_i = rint(e_i * C) from the truncated e_i with a rigorous interval test (2 fp64 FMAs);
@@ -29,7 +29,7 @@ constexpr int F_C_CAP = 256;
 constexpr int F_PIECES = 9;          // bulk-copy pieces per row (3 * FT float4 each, 24 KB)
 constexpr int F_MIN_VOCAB = 256;     // below this the exact kernel is used
 constexpr float F_BAND_EPS = 0.0009765625f;   // 2^-10 half-width (in log units) of the exact-list band
-constexpr uint32_t F_TOP = 0x3F800000u;       // bit pattern of 1.0f = e of the row maximum
+constexpr uint32_t F_TOP = 0x3FF00000u;       // high word of the double 1.0 = e of the row maximum
 
 // hand-over reasons (status bits 8..15, diagnostics only)
 enum { F_WHY_EST = 1, F_WHY_BAND = 2, F_WHY_VERIFY = 3, F_WHY_RANK = 4, F_WHY_ULIST = 5, F_WHY_BUCKET = 6 };
@@ -91,10 +91,18 @@ __device__ __forceinline__ void f_mbar_wait(u64* bar, uint32_t parity) {
       "}\n" :: "r"(f_smem_addr(bar)), "r"(parity) : "memory");
 }
 
-// hist[bin] += q unless q == 0, as one predicated shared-memory reduction (no branch)
+// The exp pass leaves, in place of each kept logit, the HIGH 32 BITS of its fp64 e (sign, exponent,
+// 20 mantissa bits = e truncated toward zero to 2^-20 relative): a monotone 32-bit key that turns
+// back into a double without touching the conversion unit.  It is carried in the float4 row as a bit
+// pattern (always a positive, non-NaN float pattern, 0 = not kept).
+__device__ __forceinline__ float f_pack_e(double e) { return __int_as_float(__double2hiint(e)); }
+__device__ __forceinline__ double f_unpack_e(float w) { return __hiloint2double(__float_as_int(w), 0); }
+
+// hist[bin] += q, unconditionally: q == 0 (not kept) adds nothing, and without a predicate the
+// compiler batches the eight address computations and reductions of an iteration (no branches).
 __device__ __forceinline__ void f_hist_add(uint32_t* hist, uint32_t bin, uint32_t q) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}"
-               :: "r"(f_smem_addr(hist + bin)), "r"(q) : "memory");
+  // not-kept elements all map to one bucket index: spread their (zero) adds over the lanes' own buckets
+  atomicAdd(hist + (q ? bin : (threadIdx.x & (F_NB - 1))), q);
 }
 
 // queue a row for the exact kernel: slow_ws = {count, done, rows...}
@@ -270,7 +278,32 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       int c1 = c0 + PC;
       if (c1 > 1 + NI) c1 = 1 + NI;
       if (c0 < c1) { f_mbar_wait(&sc->bar[k], (parity >> k) & 1u); parity ^= (1u << k); }
-      for (int c = c0 + tid; c < c1; c += FT) online4(w4[c], 4 * c - mis);
+      // a piece is 3 float4 per thread: load all three, then run the three dependent chains interleaved
+      const int ca = c0 + tid, cb = ca + FT, cc = cb + FT;
+      if (cc < c1) {
+        const float4 va = w4[ca], vb = w4[cb], vc = w4[cc];
+        const float ma = fmaxf(fmaxf(va.x, va.y), fmaxf(va.z, va.w));
+        const float mb = fmaxf(fmaxf(vb.x, vb.y), fmaxf(vb.z, vb.w));
+        const float mc = fmaxf(fmaxf(vc.x, vc.y), fmaxf(vc.z, vc.w));
+        const float cm = fmaxf(ma, fmaxf(mb, mc));
+        kmin = fminf(kmin, fminf(fminf(fminf(va.x, va.y), fminf(va.z, va.w)),
+                                 fminf(fminf(fminf(vb.x, vb.y), fminf(vb.z, vb.w)), fminf(fminf(vc.x, vc.y), fminf(vc.z, vc.w)))));
+        if (cm > tm) {                                       // rare after the first pieces
+          ts *= f_ex2((tm - cm) * c2);
+          tm = cm;
+          ntc = -cm * c2;
+          const float4 vv = (ma == cm) ? va : (mb == cm) ? vb : vc;
+          const int bb = 4 * ((ma == cm) ? ca : (mb == cm) ? cb : cc) - mis;
+          ti = (vv.x == cm) ? bb : (vv.y == cm) ? bb + 1 : (vv.z == cm) ? bb + 2 : bb + 3;
+        }
+        const float sa = (f_ex2(fmaf(va.x, c2, ntc)) + f_ex2(fmaf(va.y, c2, ntc))) + (f_ex2(fmaf(va.z, c2, ntc)) + f_ex2(fmaf(va.w, c2, ntc)));
+        const float sb = (f_ex2(fmaf(vb.x, c2, ntc)) + f_ex2(fmaf(vb.y, c2, ntc))) + (f_ex2(fmaf(vb.z, c2, ntc)) + f_ex2(fmaf(vb.w, c2, ntc)));
+        const float sc3 = (f_ex2(fmaf(vc.x, c2, ntc)) + f_ex2(fmaf(vc.y, c2, ntc))) + (f_ex2(fmaf(vc.z, c2, ntc)) + f_ex2(fmaf(vc.w, c2, ntc)));
+        ts += (sa + sb) + sc3;
+      } else {
+        if (ca < c1) online4(w4[ca], 4 * ca - mis);
+        if (cb < c1) online4(w4[cb], 4 * cb - mis);
+      }
     }
     pc.mark(1);                                            // L: waits + estimate over the pieces
     __syncthreads();                                       // edge chunks written by threads 0..7
@@ -392,10 +425,10 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       accl3 = __fma_rn(e3, l3 ? 1.0 : 0.0, accl3);
       if (need_count) cnt_hi += (int)h0 + (int)h1 + (int)h2 + (int)h3;
       float4 o;
-      o.x = h0 ? __double2float_rz(e0) : 0.0f;
-      o.y = h1 ? __double2float_rz(e1) : 0.0f;
-      o.z = h2 ? __double2float_rz(e2) : 0.0f;
-      o.w = h3 ? __double2float_rz(e3) : 0.0f;
+      o.x = h0 ? f_pack_e(e0) : 0.0f;
+      o.y = h1 ? f_pack_e(e1) : 0.0f;
+      o.z = h2 ? f_pack_e(e2) : 0.0f;
+      o.w = h3 ? f_pack_e(e3) : 0.0f;
       w4[c] = o;
       if (!((h0 | l0) & (h1 | l1) & (h2 | l2) & (h3 | l3))) {   // rare: inside the guard band
         if (!(h0 | l0)) band_push(b, e0);
@@ -446,11 +479,11 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     }
     const double C = __ddiv_rn((double)R, S);                // :146
     const double C_lo = C * (1.0 - 2.220446049250313e-16);
-    const double C_hi = C * (1.0 + 1.1920928955078125e-07 + 9.094947017729282e-13);
+    const double C_hi = C * (1.0 + 9.5367431640625e-07 + 9.094947017729282e-13);   // e < e_trunc * (1 + 2^-20)
     // bucket shift: every kept element (certain or band) has e >= e(max(kappa_lo_pred, lowest logit)) > 0
     int SH;
     {
-      const float e_min = __double2float_rz(ns_exp64_core(a_of(fmaxf(kappa_lo_pred, key_min)), tab));
+      const float e_min = f_pack_e(ns_exp64_core(a_of(fmaxf(kappa_lo_pred, key_min)), tab));
       const uint32_t span = F_TOP - __float_as_uint(e_min);
       SH = 0;
       while ((span >> SH) > (uint32_t)(F_NB - 1)) ++SH;
@@ -463,7 +496,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     };
     // bin width decided from the truncated e alone; returns false when it is not decidable
     auto quick_mass = [&](float e32, uint32_t* q) -> bool {
-      const double ed = (double)e32;
+      const double ed = f_unpack_e(e32);
       const uint32_t ql = (uint32_t)ns_double_as_u64(__fma_rn(ed, C_lo, magic));
       const uint32_t qh = (uint32_t)ns_double_as_u64(__fma_rn(ed, C_hi, magic));
       *q = ql;
@@ -472,25 +505,35 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
 
     pc.mark(4);                                            // FIX: sums, band, verification, constants
     // ------------------------------------------------------------------ P2: integer bin widths
-    for (int c = tid; c < W4; c += FT) {
-      const float4 v = w4[c];
-      const int b = 4 * c - mis;
-      uint32_t q0, q1, q2, q3;
-      const bool k0 = quick_mass(v.x, &q0), k1 = quick_mass(v.y, &q1), k2 = quick_mass(v.z, &q2), k3 = quick_mass(v.w, &q3);
-      if (k0 & k1 & k2 & k3) {                               // e32 == 0 (not kept) yields q == 0: skipped
-        f_hist_add(hist, bin_of_e(v.x) & (F_NB - 1), q0);    // q == 0 (not kept): predicated off
-        f_hist_add(hist, bin_of_e(v.y) & (F_NB - 1), q1);
-        f_hist_add(hist, bin_of_e(v.z) & (F_NB - 1), q2);
-        f_hist_add(hist, bin_of_e(v.w) & (F_NB - 1), q3);
-      } else {
-        const float ev[4] = {v.x, v.y, v.z, v.w};
-        const uint32_t qv[4] = {q0, q1, q2, q3};
-        const bool kv[4] = {k0, k1, k2, k3};
+    // two float4 per iteration: 8 independent conversion + FMA chains in flight per thread
+    auto p2_slow = [&](const float4 v, const int b, const uint32_t* qv, const bool* kv) {
+      const float ev[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (kv[j]) { if (qv[j]) atomicAdd(&hist[bin_of_e(ev[j])], qv[j]); }
-          else { const int s = atomicAdd(&sc->u_n, 1); if (s < F_U_CAP) ulist[s] = b + j; }
-        }
+      for (int j = 0; j < 4; ++j) {
+        if (kv[j]) { if (qv[j]) atomicAdd(&hist[bin_of_e(ev[j])], qv[j]); }
+        else { const int s = atomicAdd(&sc->u_n, 1); if (s < F_U_CAP) ulist[s] = b + j; }
+      }
+    };
+    for (int c = tid; c < W4; c += 2 * FT) {
+      const float4 v = w4[c];
+      const float4 w = (c + FT < W4) ? w4[c + FT] : make_float4(0.f, 0.f, 0.f, 0.f);   // e32 == 0: no-op
+      const int b = 4 * c - mis;
+      uint32_t q[8];
+      bool k[8];
+      k[0] = quick_mass(v.x, &q[0]); k[1] = quick_mass(v.y, &q[1]); k[2] = quick_mass(v.z, &q[2]); k[3] = quick_mass(v.w, &q[3]);
+      k[4] = quick_mass(w.x, &q[4]); k[5] = quick_mass(w.y, &q[5]); k[6] = quick_mass(w.z, &q[6]); k[7] = quick_mass(w.w, &q[7]);
+      if (k[0] & k[1] & k[2] & k[3] & k[4] & k[5] & k[6] & k[7]) {   // e32 == 0 (not kept) yields q == 0
+        f_hist_add(hist, bin_of_e(v.x) & (F_NB - 1), q[0]);  // q == 0: predicated off
+        f_hist_add(hist, bin_of_e(v.y) & (F_NB - 1), q[1]);
+        f_hist_add(hist, bin_of_e(v.z) & (F_NB - 1), q[2]);
+        f_hist_add(hist, bin_of_e(v.w) & (F_NB - 1), q[3]);
+        f_hist_add(hist, bin_of_e(w.x) & (F_NB - 1), q[4]);
+        f_hist_add(hist, bin_of_e(w.y) & (F_NB - 1), q[5]);
+        f_hist_add(hist, bin_of_e(w.z) & (F_NB - 1), q[6]);
+        f_hist_add(hist, bin_of_e(w.w) & (F_NB - 1), q[7]);
+      } else {
+        p2_slow(v, b, q, k);
+        p2_slow(w, b + 4 * FT, q + 4, k + 4);
       }
     }
     pc.mark(5);                                            // P2 loop
@@ -503,7 +546,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     }
     if (tid < nband && band[tid].kept) {
       const double e = band[tid].e;
-      atomicAdd(&hist[bin_of_e(__double2float_rz(e))], (uint32_t)__double2ll_rn(e * C));
+      atomicAdd(&hist[bin_of_e(f_pack_e(e))], (uint32_t)__double2ll_rn(e * C));
     }
     __syncthreads();
 
@@ -579,7 +622,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
         }
       }
       if (tid < nband && band[tid].kept) {
-        const float e32 = __double2float_rz(band[tid].e);
+        const float e32 = f_pack_e(band[tid].e);
         if (bin_of_e(e32) == (uint32_t)tb) {
           const int s = atomicAdd(&sc->c_n, 1);
           if (s < F_C_CAP) {
@@ -646,7 +689,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       if (select_tau(R, &j, &bj, &wj)) {
         truncated = true;
         trunc_e.ebits = __float_as_uint(words[j + mis]);
-        for (int k = 0; k < nband; ++k) if (band[k].id == j) trunc_e.ebits = __float_as_uint(__double2float_rz(band[k].e));
+        for (int k = 0; k < nband; ++k) if (band[k].id == j) trunc_e.ebits = __float_as_uint(f_pack_e(band[k].e));
         trunc_e.id = j; trunc_e.key = g[j] + 0.0f;
         slack = R - bj;
       } else slack = 0;
@@ -683,7 +726,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       float e32t = words[tok + mis];
       if (!(e32t > 0.0f)) {
         for (int k = 0; k < nband; ++k)
-          if (band[k].id == tok && band[k].kept) e32t = __double2float_rz(band[k].e);
+          if (band[k].id == tok && band[k].kept) e32t = f_pack_e(band[k].e);
       }
       bool in_range = e32t > 0.0f;
       u64 bs = 0, ws = top_mass;
