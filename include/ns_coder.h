@@ -107,6 +107,10 @@ typedef struct ns_ac_params {
   /* optional profiling counters (16 x uint64, zeroed by the caller): SM-clock cycles spent per
      phase of the throughput kernel, summed over thread 0 of every CTA; [15] counts rows */
   uint64_t* prof;
+  /* optional, encode only: per-step statistics of the reference (arithmetic.py:192-198), [B,3] fp64 =
+     log p(selected token), KL(q_hat || p) in bits, entropy of the tempered distribution in bits.
+     Requesting them routes the step through the exact kernel. */
+  double* stats;
 } ns_ac_params;
 
 int ns_version(void);

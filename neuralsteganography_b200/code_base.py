@@ -21,16 +21,18 @@ from .trunk import StaticGPT2
 def encode_arithmetic(model, enc, message: Sequence[int], context: Sequence[int], finish_sent: bool = False,
                       device: str = "cuda", temp: float = 1.0, precision: int = 16, topk: int = 50000,
                       max_len: int = 1024):
-    """-> (tokens, avg_NLL, avg_KL, words_per_bit, avg_Hq); the four statistics are ``nan`` on the device
-    path except ``words_per_bit`` (they are host diagnostics of the reference, arithmetic.py:192-199)."""
+    """-> (tokens, avg_NLL, avg_KL, words_per_bit, avg_Hq) like the reference (arithmetic.py:212-217).
+    The statistics are accumulated on the device, one [1,3] read per step (this entry point is the
+    single-stream research path; the batched provider does not compute them)."""
     gen = StegoGenerator(model, 1, max_len=max_len, precision=precision, temp=temp, topk=topk,
-                         finish_sent=finish_sent, device=device)
+                         finish_sent=finish_sent, device=device, use_graph=False, collect_stats=True)
     ctx = torch.tensor(list(context)[-1022:], dtype=torch.long)
     tokens = gen.encode(ctx, [list(map(int, message))])[0]
     used = int(gen.coder.cursor[0].item())
-    coded = len(tokens)
+    n = max(1, gen.stats_steps)
     nan = float("nan")
-    return tokens, nan, nan, (coded / used if used else nan), nan
+    lp, kl, hq = [float(x) for x in gen.stats_sum[0].tolist()]
+    return tokens, -lp / n, kl / n, (gen.stats_steps / used if used else nan), hq / n
 
 
 def decode_arithmetic(model, enc, text, context: Sequence[int], device: str = "cuda", temp: float = 1.0,

@@ -161,6 +161,7 @@ class ArithmeticStreams:
         p.slow_ws = self.slow_ws.data_ptr()
         p.force_exact = int(self.force_exact)
         p.prof = N.ptr(getattr(self, "prof", None))
+        p.stats = N.ptr(getattr(self, "stats", None))
         return p
 
     def encode_step(self, logits: torch.Tensor) -> None:

@@ -193,6 +193,7 @@ __device__ void ac_exact_row(const ns_ac_params& P, const int row, u64* dbg_q, u
   rm.rank_form = false; rm.bound_pack = 0; rm.C = 0.0; rm.inv_sum = 0.0;
 
   // ---- P1: softmax normaliser ------------------------------------------------------------
+  double sum_e = 0.0;
   {
     double acc0 = 0.0, acc1 = 0.0;
     int i = tid;
@@ -203,6 +204,7 @@ __device__ void ac_exact_row(const ns_ac_params& P, const int row, u64* dbg_q, u
     if (i < V) acc0 += rm.e_of(keys[i]);
     const double sum = block_sum_d(acc0 + acc1, sc->red);
     rm.inv_sum = __ddiv_rn(1.0, sum);
+    sum_e = sum;
   }
 
   // ---- P2: kept set -------------------------------------------------------------------------
@@ -379,6 +381,43 @@ __device__ void ac_exact_row(const ns_ac_params& P, const int row, u64* dbg_q, u
       if (s == top_id) { nb = lo; nt = lo + ws + slack; }
       else { nb = lo + bs + slack; nt = nb + ws; }           // :175-176
     }
+    if (P.stats) {
+      // per-step statistics of the reference (arithmetic.py:131-132,192-198; utils.py:32-40):
+      // log p(selected) under the untempered softmax, KL(q_hat || p) in bits over the kept bins,
+      // entropy of the tempered distribution in bits.
+      __syncthreads();
+      const double md = (double)m;
+      double s1 = sum_e;
+      if (!rm.unit_temp) {
+        double acc = 0.0;
+        for (int i = tid; i < V; i += NT) acc += ns_exp64_neg((double)keys[i] - md, tab);
+        s1 = block_sum_d(acc, sc->red);
+      }
+      const double ln_s1 = log(s1), ln_se = log(sum_e);
+      double kl = 0.0, ent = 0.0;
+      for (int i = tid; i < V; i += NT) {
+        const float k = keys[i];
+        const double a = rm.a_of(k);
+        const double e = ns_exp64_neg(a, tab);
+        const double pt = e * rm.inv_sum;
+        if (pt != 0.0) ent += pt * (a - ln_se) / 0.69315;                  // utils.py:38
+        u64 w = rm.mass(k, i);
+        if (truncated && pack_of(k, i) <= trunc_pack) w = 0;
+        if (i == top_id) w += slack;                                       // :158
+        if (w != 0) {
+          const double qh = (double)w / (double)R;                         // :195
+          kl += qh * (log(qh) - (((double)k - md) - ln_s1)) / 0.69315;     // utils.py:33
+        }
+      }
+      kl = block_sum_d(kl, sc->red);
+      ent = block_sum_d(ent, sc->red);
+      if (tid == 0) {
+        double* st = P.stats + (size_t)row * 3;
+        st[0] = ((double)keys[token] - md) - ln_s1;                        // log_probs[selection], :193
+        st[1] = kl;
+        st[2] = -ent;
+      }
+    }
     if (tid == 0) finish_encode(P, row, slot, token, nb, nt, k0, Q, cursor, mlen);
   } else {
     // decode: rank of the observed token = mass in front of it (:298)
@@ -506,7 +545,7 @@ int dispatch(const ns_ac_params* p, u64* dbg_q, u64* dbg_meta, void* stream) {
   if (rc != NS_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (p->precision > 31) return launch_exact<MODE, u64>(p, dbg_q, dbg_meta, nullptr, st);
-  if (MODE == MODE_DEBUG || p->slow_ws == nullptr || p->force_exact || p->V < F_MIN_VOCAB)
+  if (MODE == MODE_DEBUG || p->slow_ws == nullptr || p->force_exact || p->V < F_MIN_VOCAB || p->stats != nullptr)
     return launch_exact<MODE, uint32_t>(p, dbg_q, dbg_meta, nullptr, st);
   // throughput path: fast kernel, then the exact kernel on whatever it handed over
   rc = (p->temp == 1.0) ? launch_fast<true, MODE == MODE_DEBUG ? MODE_ENC : MODE>(p, st)

@@ -21,7 +21,8 @@ class StegoGenerator:
 
     def __init__(self, hf_model, batch: int, *, max_len: int = 256, precision: int = 16, temp: float = 1.0,
                  topk: int = 50000, finish_sent: bool = False, sent_end: Optional[torch.Tensor] = None,
-                 device="cuda", use_graph: bool = True, trunk_dtype: torch.dtype = torch.float32):
+                 device="cuda", use_graph: bool = True, trunk_dtype: torch.dtype = torch.float32,
+                 collect_stats: bool = False):
         self.B = int(batch)
         self.device = torch.device(device)
         self.trunk = StaticGPT2(hf_model, batch, max_len=max_len, device=device, dtype=trunk_dtype)
@@ -32,13 +33,22 @@ class StegoGenerator:
         self.logits = torch.zeros(self.B, self.V, dtype=torch.float32, device=self.device)
         self._rows = torch.arange(self.B, device=self.device)
         self.steps_run = 0
+        self.collect_stats = bool(collect_stats)        # a6: NLL / KL / entropy sums (exact kernel, eager loop)
+        self.stats_sum = torch.zeros(self.B, 3, dtype=torch.float64, device=self.device)
+        self.stats_steps = 0
 
     # one loop iteration: coder on the current logits, then the trunk on the token just fixed
     def _iter(self, coder: ArithmeticStreams, decode: bool) -> None:
         if decode:
             coder.decode_step(self.logits)
         else:
+            if self.collect_stats:
+                coding = (coder.phase == 0).to(torch.float64)[:, None]      # tail / finished streams add nothing
+                coder.stats.zero_()
             coder.encode_step(self.logits)
+            if self.collect_stats:
+                self.stats_sum += coder.stats * coding
+                self.stats_steps += int(coding.sum().item() > 0)
         last = (coder.ntok.long() - 1).clamp(min=0)
         prev = coder.tokens[self._rows, last].long().clamp(min=0)      # finished streams feed a stale token
         self.logits.copy_(self.trunk.step(prev))
@@ -74,6 +84,9 @@ class StegoGenerator:
         room = self.max_len - int(contexts.shape[-1]) - 1
         coder = ArithmeticStreams(self.B, self.V, device=self.device, token_cap=max(1, room), **self.kw)
         coder.set_messages(messages)
+        if self.collect_stats:
+            coder.stats = torch.zeros(self.B, 3, dtype=torch.float64, device=self.device)
+            self.stats_sum.zero_(); self.stats_steps = 0
         self._prefill(contexts)
         self._run(coder, False, room, poll_every)
         self.coder = coder

@@ -223,3 +223,27 @@ def test_rejects_cpu_tensors_and_bad_shapes():
         st.encode_step(torch.zeros(2, 2048))
     with pytest.raises(NativeLibraryError):
         st.encode_step(torch.zeros(3, 2048, device="cuda"))
+
+
+def test_device_statistics_match_oracle():
+    """a6: log p(selected), KL(q_hat||p) and entropy per step (code_base/arithmetic.py:192-198) vs the oracle."""
+    V, B = 50257, 3
+    pool = logits_pool(123, 6, V, 3.0)
+    from gpu_util import PoolLogits
+    fn = PoolLogits(pool, B)
+    for temp, topk, precision in ((0.9, 300, 26), (1.0, V, 26)):
+        msgs = [message_bits(60 + r, 64).tolist() for r in range(B)]
+        st = _streams(B, V, precision=precision, temp=temp, topk=topk, token_cap=32)
+        st.stats = torch.zeros(B, 3, dtype=torch.float64, device="cuda")
+        st.set_messages(msgs)
+        lo = [0] * B; hi = [1 << precision] * B; cur = [0] * B
+        for t in range(4):
+            st.encode_step(fn(t))
+            torch.cuda.synchronize()
+            got = st.stats.cpu().numpy()
+            for r in range(B):
+                tr, ncur, stats, _ = O.encode_step(rows_for(pool, r)(t), lo[r], hi[r], msgs[r], cur[r], temp=temp,
+                                                   precision=precision, topk=topk, want_stats=True)
+                assert int(st.tokens[r, t]) == tr.token
+                np.testing.assert_allclose(got[r], stats, rtol=1e-9, atol=1e-12)
+                lo[r], hi[r], cur[r] = tr.lo, tr.hi, ncur
