@@ -29,7 +29,7 @@ constexpr int F_C_CAP = 256;
 constexpr int F_PIECES = 9;          // bulk-copy pieces per row (3 * FT float4 each, 24 KB)
 constexpr int F_MIN_VOCAB = 256;     // below this the exact kernel is used
 constexpr float F_BAND_EPS = 0.0009765625f;   // 2^-10 half-width (in log units) of the exact-list band
-constexpr uint32_t F_TOP = 0x3FF00000u;       // high word of the double 1.0 = e of the row maximum
+constexpr uint32_t F_TOP = 0xFF000000u;       // packed e of the row maximum (e == 1.0)
 
 // hand-over reasons (status bits 8..15, diagnostics only)
 enum { F_WHY_EST = 1, F_WHY_BAND = 2, F_WHY_VERIFY = 3, F_WHY_RANK = 4, F_WHY_ULIST = 5, F_WHY_BUCKET = 6 };
@@ -51,6 +51,7 @@ struct FScal {
   float sum32; int remax; float M; int top_id;
   int band_n; int u_n; int c_n; int bail;
   u64 band_cut_int;
+  int band_kept_n; int sh;
   int sel_bin; u64 sel_prefix;
   int res_idx; u64 res_before; u64 res_w; int res_found;
   float kappa_lo, kappa_hi, clamp_key; int band_E;
@@ -91,12 +92,18 @@ __device__ __forceinline__ void f_mbar_wait(u64* bar, uint32_t parity) {
       "}\n" :: "r"(f_smem_addr(bar)), "r"(parity) : "memory");
 }
 
-// The exp pass leaves, in place of each kept logit, the HIGH 32 BITS of its fp64 e (sign, exponent,
-// 20 mantissa bits = e truncated toward zero to 2^-20 relative): a monotone 32-bit key that turns
-// back into a double without touching the conversion unit.  It is carried in the float4 row as a bit
-// pattern (always a positive, non-NaN float pattern, 0 = not kept).
-__device__ __forceinline__ float f_pack_e(double e) { return __int_as_float(__double2hiint(e)); }
-__device__ __forceinline__ double f_unpack_e(float w) { return __hiloint2double(__float_as_int(w), 0); }
+// The exp pass leaves, in place of each kept logit, a 32-bit truncation of its fp64 e: the double's
+// bits 59..28 (low 8 exponent bits + 24 mantissa bits; for 2^-255 < e <= 1 the four bits above are the
+// constant 0011).  It is monotone in e, accurate to 2^-24 (toward zero), and turns back into a double
+// with two shifts -- no trip through the conversion unit.  Carried in the float4 row as a bit pattern;
+// 0 = not kept (unpacks to 2^-255: its bin width rounds to 0).
+__device__ __forceinline__ float f_pack_e(double e) {
+  return __uint_as_float(__funnelshift_l((uint32_t)__double2loint(e), (uint32_t)__double2hiint(e), 4));
+}
+__device__ __forceinline__ double f_unpack_e(float w) {
+  const uint32_t b = __float_as_uint(w);
+  return __hiloint2double((int)__funnelshift_r(b, 0x3u, 4), (int)(b << 28));
+}
 
 // hist[bin] += q, unconditionally: q == 0 (not kept) adds nothing, and without a predicate the
 // compiler batches the eight address computations and reductions of an iteration (no branches).
@@ -110,6 +117,27 @@ __device__ __forceinline__ void hand_over(const ns_ac_params& P, int32_t* slow_w
   const int s = atomicAdd(&slow_ws[0], 1);
   slow_ws[2 + s] = row;
   if (P.status) atomicOr(&P.status[row], NS_ST_EST_RETRY | (why << 8));   // informational
+}
+
+// max of a and min of b in one pass (one pair of barriers)
+__device__ __forceinline__ void f_reduce_maxmin(u64& a, u64& b, u64* scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const u64 x = __shfl_xor_sync(0xffffffffu, a, o), y = __shfl_xor_sync(0xffffffffu, b, o);
+    a = x > a ? x : a;
+    b = y < b ? y : b;
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { scratch[threadIdx.x >> 5] = a; scratch[FW + (threadIdx.x >> 5)] = b; }
+  __syncthreads();
+  u64 ra = scratch[0], rb = scratch[FW];
+#pragma unroll
+  for (int w = 1; w < FW; ++w) {
+    const u64 x = scratch[w], y = scratch[FW + w];
+    ra = x > ra ? x : ra;
+    rb = y < rb ? y : rb;
+  }
+  a = ra; b = rb;
 }
 
 template <class Op>
@@ -240,7 +268,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
           f_bulk_g2s(dst + (size_t)c0 * 16, src + (size_t)c0 * 16, (uint32_t)n * 16u, &sc->bar[k]);
         }
       }
-      sc->band_n = 0; sc->u_n = 0; sc->c_n = 0; sc->bail = 0; sc->band_cut_int = 0; sc->remax = 0;
+      sc->band_n = 0; sc->u_n = 0; sc->c_n = 0; sc->bail = 0; sc->band_cut_int = 0; sc->remax = 0; sc->band_kept_n = 0;
     }
     // the two edge chunks may straddle the row ends: plain loads, -inf padding
     if (tid < 8) {
@@ -320,12 +348,13 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
         if (v.w > -INFINITY) kmin = fminf(kmin, v.w);
       }
     }
-    const u64 pmax = f_reduce_u(pack_of(tm + 0.0f, ti), OpMaxU(), sc->red);
+    u64 pmax = pack_of(tm + 0.0f, ti), pmin_k = pack_of(kmin, 0);
+    f_reduce_maxmin(pmax, pmin_k, sc->red);
     float M = key_of_pack(pmax);
     int top_id = id_of_pack(pmax);
     float ssum = f_sum_f(ts * f_ex2((tm - M) * c2), sc->red);
     // lowest interior logit (-inf if the caller masked tokens with -inf: then the cutoff bounds the range)
-    const float key_min = key_of_pack(f_reduce_u(pack_of(kmin, 0), OpMinU(), sc->red));
+    const float key_min = key_of_pack(pmin_k);
     // forbidden tokens (code_base/arithmetic.py:124-125): probability exactly 0
     if (tid == 0) {
       int remax = 0;
@@ -446,16 +475,17 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     const int nband = sc->band_n;
     const double band_scale = scalbn(1.0, 52 - sc->band_E);
     // ------------------------------------------------------------------ FIX: exact classification
-    int my_band_kept = 0;
+    // band elements, the verification of the provisional split and the bucket range run on different
+    // lanes at the same time; one barrier publishes all of it.
+    const float kappa_lo_pred = nextafterf(kappa_lo, -INFINITY);
     if (nband <= F_BAND_CAP && tid < nband) {
       const double e = band[tid].e;
       const bool k = (e * inv) >= thr;                       // p_i >= 1/range, :69
       band[tid].kept = k ? 1 : 0;
-      my_band_kept = k ? 1 : 0;
-      if (!k) atomicAdd(&sc->band_cut_int, (u64)__double2ull_rz(e * band_scale));   // exact, order-free
+      if (k) atomicAdd(&sc->band_kept_n, 1);
+      else atomicAdd(&sc->band_cut_int, (u64)__double2ull_rz(e * band_scale));   // exact, order-free
     }
-    const float kappa_lo_pred = nextafterf(kappa_lo, -INFINITY);
-    if (tid == 0) {
+    if (tid == FT - 64) {
       // the provisional split is valid iff exp is monotone and both band edges classify as assumed
       const double e_hi = ns_exp64_core(a_of(kappa_hi), tab);
       const double e_lo = ns_exp64_core(a_of(kappa_lo_pred), tab);
@@ -464,8 +494,16 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       else if (!((e_hi * inv) >= thr) || ((e_lo * inv) >= thr)) bail = F_WHY_VERIFY;
       sc->bail = bail;
     }
-    const u64 n_band_kept = f_reduce_u((u64)my_band_kept, OpAddU(), sc->red);   // (barriers inside)
-    const u64 cand = n_hi + n_band_kept;                     // only counted when topk < V
+    if (tid == FT - 96) {
+      // bucket shift: every kept element (certain or band) has e >= e(max(kappa_lo_pred, lowest logit)) > 0
+      const float e_min = f_pack_e(ns_exp64_core(a_of(fmaxf(kappa_lo_pred, key_min)), tab));
+      const uint32_t span = F_TOP - __float_as_uint(e_min);
+      int sh = 0;
+      while ((span >> sh) > (uint32_t)(F_NB - 1)) ++sh;
+      sc->sh = sh;
+    }
+    __syncthreads();
+    const u64 cand = n_hi + (u64)sc->band_kept_n;            // only counted when topk < V
     const double sum_bc = (double)sc->band_cut_int * scalbn(1.0, sc->band_E - 52);
     const double S = (sum_all - sum_lo) - sum_bc;            // sum of the kept e_i
     // kept set must have 2..topk members, else the reference switches to rank form (:75).  The row
@@ -479,15 +517,8 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     }
     const double C = __ddiv_rn((double)R, S);                // :146
     const double C_lo = C * (1.0 - 2.220446049250313e-16);
-    const double C_hi = C * (1.0 + 9.5367431640625e-07 + 9.094947017729282e-13);   // e < e_trunc * (1 + 2^-20)
-    // bucket shift: every kept element (certain or band) has e >= e(max(kappa_lo_pred, lowest logit)) > 0
-    int SH;
-    {
-      const float e_min = f_pack_e(ns_exp64_core(a_of(fmaxf(kappa_lo_pred, key_min)), tab));
-      const uint32_t span = F_TOP - __float_as_uint(e_min);
-      SH = 0;
-      while ((span >> SH) > (uint32_t)(F_NB - 1)) ++SH;
-    }
+    const double C_hi = C * (1.0 + 5.960464477539063e-08 + 9.094947017729282e-13);   // e < e_trunc * (1 + 2^-24)
+    const int SH = sc->sh;
     auto bin_of_e = [&](float e32) -> uint32_t { return (F_TOP - __float_as_uint(e32)) >> SH; };
     // exact bin width from the original logit (same formula as the exact kernel)
     auto exact_mass = [&](int id) -> uint32_t {
@@ -724,11 +755,11 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       if (tok < 0 || tok >= V) tok = top_id;
       // is the observed token in the kept set, and in which bucket?
       float e32t = words[tok + mis];
-      if (!(e32t > 0.0f)) {
+      if (__float_as_uint(e32t) == 0u) {
         for (int k = 0; k < nband; ++k)
           if (band[k].id == tok && band[k].kept) e32t = f_pack_e(band[k].e);
       }
-      bool in_range = e32t > 0.0f;
+      bool in_range = __float_as_uint(e32t) != 0u;
       u64 bs = 0, ws = top_mass;
       int token = top_id;
       if (in_range) {
