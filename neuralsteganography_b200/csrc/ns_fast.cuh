@@ -633,23 +633,33 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     auto collect = [&](int tb) -> int {
       if (tid == 0) sc->c_n = 0;
       __syncthreads();
-      for (int c = tid; c < W4; c += FT) {
-        const float4 v = w4[c];
-        const bool m0 = bin_of_e(v.x) == (uint32_t)tb, m1 = bin_of_e(v.y) == (uint32_t)tb;
-        const bool m2 = bin_of_e(v.z) == (uint32_t)tb, m3 = bin_of_e(v.w) == (uint32_t)tb;
-        if (m0 | m1 | m2 | m3) {                             // e32 == 0 maps far outside the histogram
-          const float ev[4] = {v.x, v.y, v.z, v.w};
-          const bool mv[4] = {m0, m1, m2, m3};
+      auto gather4 = [&](const float4 v, const int c) {
+        const float ev[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (mv[j]) {
-              const int id = 4 * c - mis + j;
-              uint32_t q;
-              if (!quick_mass(ev[j], &q)) q = exact_mass(id);
-              const int s = atomicAdd(&sc->c_n, 1);
-              if (s < F_C_CAP) { clist[s].ebits = __float_as_uint(ev[j]); clist[s].id = id; clist[s].w = q; clist[s].key = 0.0f; }
-            }
+        for (int j = 0; j < 4; ++j) {
+          if (bin_of_e(ev[j]) == (uint32_t)tb) {             // packed 0 (not kept) maps far outside the histogram
+            const int id = 4 * c - mis + j;
+            uint32_t q;
+            if (!quick_mass(ev[j], &q)) q = exact_mass(id);
+            const int s = atomicAdd(&sc->c_n, 1);
+            if (s < F_C_CAP) { clist[s].ebits = __float_as_uint(ev[j]); clist[s].id = id; clist[s].w = q; clist[s].key = 0.0f; }
           }
+        }
+      };
+      auto hit4 = [&](const float4 v) -> bool {
+        return (bin_of_e(v.x) == (uint32_t)tb) | (bin_of_e(v.y) == (uint32_t)tb) | (bin_of_e(v.z) == (uint32_t)tb) | (bin_of_e(v.w) == (uint32_t)tb);
+      };
+      // three float4 per iteration: the loads and the twelve bucket tests overlap, matches are rare
+      for (int c = tid; c < W4; c += 3 * FT) {
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 va = w4[c];
+        const float4 vb = (c + FT < W4) ? w4[c + FT] : zero;
+        const float4 vc = (c + 2 * FT < W4) ? w4[c + 2 * FT] : zero;
+        const bool ha = hit4(va), hb = hit4(vb), hc = hit4(vc);
+        if (ha | hb | hc) {
+          if (ha) gather4(va, c);
+          if (hb) gather4(vb, c + FT);
+          if (hc) gather4(vc, c + 2 * FT);
         }
       }
       if (tid < nband && band[tid].kept) {
@@ -665,14 +675,6 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       __syncthreads();
       int n = sc->c_n;
       if (n > F_C_CAP) return -1;                            // dense bucket: the exact kernel redoes the row
-      // entries sharing a truncated e need the original logit to be ordered
-      for (int c = tid; c < n; c += FT) {
-        const uint32_t eb = clist[c].ebits;
-        bool dup = false;
-        for (int o = 0; o < n; ++o) dup |= (o != c) && (clist[o].ebits == eb);
-        if (dup) clist[c].key = g[clist[c].id] + 0.0f;
-      }
-      __syncthreads();
       return n;
     };
     // coder order: larger e first; equal truncated e: larger logit first; equal logits: lower id first
@@ -682,8 +684,15 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       return x.id < y.id;
     };
     auto resolve = [&](int n, u64 prefix, bool by_token, u64 tau, int want_id) -> bool {
+      // entries sharing a packed e (rare with 24 mantissa bits) need the original logit to be ordered
+      for (int c = tid; c < n; c += FT) {
+        const uint32_t eb = clist[c].ebits;
+        bool d = false;
+        for (int o = 0; o < n; ++o) d |= (o != c) && (clist[o].ebits == eb);
+        if (d) clist[c].key = g[clist[c].id] + 0.0f;
+      }
       if (tid == 0) sc->res_found = 0;
-      __syncthreads();
+      __syncthreads();                                       // keys and the reset are visible
       for (int c = tid; c < n; c += FT) {
         const CandEntry me = clist[c];
         u64 before = prefix;
