@@ -34,6 +34,9 @@ PRECISION = 26
 TEMP = 1.0
 MSG_BITS = 4096
 ALGO_BYTES_PER_TOKEN = 4 * V + 32          # SURVEY.md 8d / DESIGN.md
+# dram__bytes_read.sum + dram__bytes_write.sum of ac_fast_kernel from one `ncu --set full` capture
+# (592 rows: 119.27 MB + 7.20 MB, profiles/r1_final_fast_ncu_summary.txt), per row
+NCU_DRAM_BYTES_PER_TOKEN = (119269888 + 7197184) / 592
 METRIC = "coder_tokens_per_sec"
 WORKLOAD = "configs[2]: coder-only batch, 4096 streams x 50257 fp32 logits per GPU, full distribution, precision 26, temp 1.0"
 
@@ -310,7 +313,8 @@ def run_gpu_arm(args):
             "decode_tokens_per_sec": tokens / (dms * 1e-3),
             "live_streams_at_end": live, "roundtrip_ok": bool(rt_ok),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "ac_fast_kernel<unit_temp, ENC>",
+                         "traffic": NCU_DRAM_BYTES_PER_TOKEN * B, "traffic_source": "ncu capture of 592 rows, scaled per row",
+                         "peak_source": peak_src, "kernel": "ac_fast_kernel<unit_temp, ENC>",
                          "algorithmic_bytes_per_token": ALGO_BYTES_PER_TOKEN},
             "cpu_baseline": cpu,
             "e2e": {"value": world * B * e2e_steps / (ems * 1e-3), "unit": "tokens/s",
