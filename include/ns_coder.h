@@ -111,6 +111,13 @@ typedef struct ns_ac_params {
      log p(selected token), KL(q_hat || p) in bits, entropy of the tempered distribution in bits.
      Requesting them routes the step through the exact kernel. */
   double* stats;
+  /* Streaming variant of the throughput kernel (several CTAs per SM, no row in shared memory, no
+     vocabulary limit): per-CTA scratch rows in global memory, scratch_slots rows of scratch_stride
+     bytes (16-byte multiple, >= 4*(V+8)).  Used when variant == 1 and scratch is given. */
+  void* scratch;
+  int64_t scratch_stride;
+  int32_t scratch_slots;
+  int32_t variant;
 } ns_ac_params;
 
 int ns_version(void);

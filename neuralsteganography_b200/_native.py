@@ -48,6 +48,7 @@ class AcParams(C.Structure):
         ("out_bits", C.c_void_p), ("out_stride", C.c_int64), ("out_len", C.c_void_p),
         ("nbits_out", C.c_void_p), ("trace", C.c_void_p),
         ("slow_ws", C.c_void_p), ("force_exact", C.c_int32), ("prof", C.c_void_p), ("stats", C.c_void_p),
+        ("scratch", C.c_void_p), ("scratch_stride", C.c_int64), ("scratch_slots", C.c_int32), ("variant", C.c_int32),
     ]
 
 

@@ -454,7 +454,25 @@ __global__ void __launch_bounds__(NT, 1) ac_step_kernel(ns_ac_params P, u64* dbg
   }
 }
 
+// the throughput kernel, compiled in its two variants (see the head of ns_fast.cuh)
+namespace nsf_smem {
+#define NSF_STREAM 0
+#define NSF_FT 512
+#define NSF_MIN_CTAS 1
 #include "ns_fast.cuh"
+#undef NSF_STREAM
+#undef NSF_FT
+#undef NSF_MIN_CTAS
+}  // namespace nsf_smem
+namespace nsf_stream {
+#define NSF_STREAM 1
+#define NSF_FT 256
+#define NSF_MIN_CTAS 2
+#include "ns_fast.cuh"
+#undef NSF_STREAM
+#undef NSF_FT
+#undef NSF_MIN_CTAS
+}  // namespace nsf_stream
 
 // ------------------------------------------------------------------------------------
 // host side
@@ -530,12 +548,24 @@ template <bool UNIT, int MODE>
 int launch_fast(const ns_ac_params* p, cudaStream_t st) {
   const int smem = FIXED_BYTES + (p->V + 8) * 4;
   static bool configured = false;
-  int rc = configure(ac_fast_kernel<UNIT, MODE>, &configured);
+  int rc = configure(nsf_smem::ac_fast_kernel<UNIT, MODE>, &configured);
   if (rc != NS_OK) return rc;
   if (p->B == 0) return NS_OK;
   const int sms = num_sms();
   const int grid = p->B < sms ? p->B : sms;
-  ac_fast_kernel<UNIT, MODE><<<grid, FT, smem, st>>>(*p, p->slow_ws);
+  nsf_smem::ac_fast_kernel<UNIT, MODE><<<grid, nsf_smem::FT, smem, st>>>(*p, p->slow_ws);
+  return check_launch();
+}
+
+// streaming variant: persistent, scratch_slots CTAs (a few per SM), shared memory only for tables and lists
+template <bool UNIT, int MODE>
+int launch_stream(const ns_ac_params* p, cudaStream_t st) {
+  static bool configured = false;
+  int rc = configure(nsf_stream::ac_fast_kernel<UNIT, MODE>, &configured);
+  if (rc != NS_OK) return rc;
+  if (p->B == 0) return NS_OK;
+  const int grid = p->B < p->scratch_slots ? p->B : p->scratch_slots;
+  nsf_stream::ac_fast_kernel<UNIT, MODE><<<grid, nsf_stream::FT, FIXED_BYTES, st>>>(*p, p->slow_ws);
   return check_launch();
 }
 
@@ -545,8 +575,15 @@ int dispatch(const ns_ac_params* p, u64* dbg_q, u64* dbg_meta, void* stream) {
   if (rc != NS_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (p->precision > 31) return launch_exact<MODE, u64>(p, dbg_q, dbg_meta, nullptr, st);
-  if (MODE == MODE_DEBUG || p->slow_ws == nullptr || p->force_exact || p->V < F_MIN_VOCAB || p->stats != nullptr)
+  if (MODE == MODE_DEBUG || p->slow_ws == nullptr || p->force_exact || p->V < nsf_smem::F_MIN_VOCAB || p->stats != nullptr)
     return launch_exact<MODE, uint32_t>(p, dbg_q, dbg_meta, nullptr, st);
+  if (p->variant == 1 && p->scratch != nullptr && p->scratch_slots > 0 && p->scratch_stride >= (int64_t)(p->V + 8) * 4 &&
+      (p->scratch_stride & 15) == 0) {
+    rc = (p->temp == 1.0) ? launch_stream<true, MODE == MODE_DEBUG ? MODE_ENC : MODE>(p, st)
+                          : launch_stream<false, MODE == MODE_DEBUG ? MODE_ENC : MODE>(p, st);
+    if (rc != NS_OK) return rc;
+    return launch_exact<MODE, uint32_t>(p, dbg_q, dbg_meta, p->slow_ws, st);
+  }
   // throughput path: fast kernel, then the exact kernel on whatever it handed over
   rc = (p->temp == 1.0) ? launch_fast<true, MODE == MODE_DEBUG ? MODE_ENC : MODE>(p, st)
                         : launch_fast<false, MODE == MODE_DEBUG ? MODE_ENC : MODE>(p, st);

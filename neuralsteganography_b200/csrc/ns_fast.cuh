@@ -19,7 +19,23 @@
 // band) queues the row in slow_ws; the exact multi-pass kernel then redoes it.  The decision only
 // depends on the row and its range, never on encode/decode, so both directions take the same path.
 
-constexpr int FT = 512;              // threads per CTA
+// This header is compiled twice (ns_coder.cu), each time inside its own namespace:
+//   NSF_STREAM 0  one CTA per SM, 512 threads, the row resident in shared memory (bulk copy);
+//   NSF_STREAM 1  several smaller CTAs per SM, nothing of the row in shared memory: the logits are
+//                 streamed from HBM (estimate) and again from L2 (exp pass), the packed e words live in a
+//                 per-CTA global scratch row that stays in L2.  Rows of different CTAs are in different
+//                 phases, so the phases that stall on one pipe overlap with those that stall on another,
+//                 and the vocabulary is no longer bounded by shared memory.
+#ifndef NSF_STREAM
+#define NSF_STREAM 0
+#endif
+#ifndef NSF_FT
+#define NSF_FT 512
+#endif
+#ifndef NSF_MIN_CTAS
+#define NSF_MIN_CTAS 1
+#endif
+constexpr int FT = NSF_FT;           // threads per CTA
 constexpr int FW = FT / 32;
 constexpr int F_NB = 2048;           // histogram buckets (u32 masses: precision <= 31)
 constexpr int F_BPT = F_NB / FT;     // buckets per thread in the scan
@@ -193,6 +209,7 @@ __device__ __forceinline__ void f_sum_ddu(double& a, double& b, u64& c, u64* scr
 
 struct FastSmem {
   double* tab; uint32_t* hist; BandEntry* band; int* ulist; CandEntry* clist; FScal* sc; float* words;
+  // NSF_STREAM: `words` is this CTA's global scratch row (16-byte aligned), else the shared-memory row
 };
 
 __device__ __forceinline__ RowMeta f_load_meta(const ns_ac_params& P, int row, int mode) {
@@ -226,6 +243,32 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
   double* tab = sm.tab; uint32_t* hist = sm.hist; BandEntry* band = sm.band; int* ulist = sm.ulist;
   CandEntry* clist = sm.clist; FScal* sc = sm.sc; float* words = sm.words;
   float4* w4 = reinterpret_cast<float4*>(words);
+  // packed-word storage: shared memory, or (stream variant) L2-resident global scratch
+  auto word_ld4 = [&](int c) -> float4 {
+#if NSF_STREAM
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(w4 + c));
+    return v;
+#else
+    return w4[c];
+#endif
+  };
+  auto word_st4 = [&](int c, const float4 v) {
+#if NSF_STREAM
+    asm volatile("st.global.cg.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(w4 + c), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+#else
+    w4[c] = v;
+#endif
+  };
+  auto word_ld1 = [&](int i) -> float {
+#if NSF_STREAM
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(words + i));
+    return v;
+#else
+    return words[i];
+#endif
+  };
   const int tid = threadIdx.x;
   const int V = P.V;
   const double temp = P.temp;
@@ -254,6 +297,38 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     const int W4 = (mis + V + 3) >> 2;                     // float4 chunks of the padded row
     const int NI = W4 - 2;                                 // interior chunks: wholly inside the row
     const int PC = 3 * FT;                                 // chunks per piece: every thread does 3 of each piece
+    (void)PC;
+#if NSF_STREAM
+    const float4* g4 = reinterpret_cast<const float4*>(g - mis);   // 16-byte aligned view of the row
+    if (tid == 0) { sc->band_n = 0; sc->u_n = 0; sc->c_n = 0; sc->bail = 0; sc->band_cut_int = 0; sc->remax = 0; sc->band_kept_n = 0; }
+    // raw chunk c of the logits row: aligned 128-bit loads, the two edge chunks element-wise with -inf padding
+    auto raw4_l = [&](int c) -> float4 {
+      float4 v;
+      if (c > 0 && c < W4 - 1) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(g4 + c));
+      } else {
+        const int b = 4 * c - mis;
+        v.x = (b >= 0 && b < V) ? g[b] : -INFINITY;
+        v.y = (b + 1 >= 0 && b + 1 < V) ? g[b + 1] : -INFINITY;
+        v.z = (b + 2 >= 0 && b + 2 < V) ? g[b + 2] : -INFINITY;
+        v.w = (b + 3 >= 0 && b + 3 < V) ? g[b + 3] : -INFINITY;
+      }
+      return v;
+    };
+    // the same with the forbidden tokens (arithmetic.py:124-125) at -inf: the logits tensor is read-only
+    const int mk0 = (P.mask_id[0] >= 0 && P.mask_id[0] < V) ? P.mask_id[0] + mis : -8;
+    const int mk1 = (P.mask_id[1] >= 0 && P.mask_id[1] < V) ? P.mask_id[1] + mis : -8;
+    auto raw4_p = [&](int c) -> float4 {
+      float4 v = raw4_l(c);
+      if (c == (mk0 >> 2) || c == (mk1 >> 2)) {
+        float* f = reinterpret_cast<float*>(&v);
+        if (c == (mk0 >> 2)) f[mk0 & 3] = -INFINITY;
+        if (c == (mk1 >> 2)) f[mk1 & 3] = -INFINITY;
+      }
+      return v;
+    };
+#else
     if (tid == 0) {
       // generic-proxy accesses of the previous row are ordered before the async-proxy writes
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -276,6 +351,9 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       const int b = 4 * c - mis + (tid & 3);
       words[4 * c + (tid & 3)] = (b >= 0 && b < V) ? g[b] : -INFINITY;
     }
+    auto raw4_l = [&](int c) -> float4 { return w4[c]; };
+    auto raw4_p = [&](int c) -> float4 { return w4[c]; };    // masks are written into the shared row after L
+#endif
     for (int i = tid; i < F_NB / 4; i += FT) reinterpret_cast<uint4*>(hist)[i] = make_uint4(0, 0, 0, 0);
     {   // prefetch this CTA's next row into L2 while this one is processed
       const int nrow = row + gridDim.x;
@@ -301,6 +379,39 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       }
       ts += (f_ex2(fmaf(v.x, c2, ntc)) + f_ex2(fmaf(v.y, c2, ntc))) + (f_ex2(fmaf(v.z, c2, ntc)) + f_ex2(fmaf(v.w, c2, ntc)));
     };
+    auto online12 = [&](const float4 va, const float4 vb, const float4 vc, const int ca, const int cb, const int cc) {
+      const float ma = fmaxf(fmaxf(va.x, va.y), fmaxf(va.z, va.w));
+      const float mb = fmaxf(fmaxf(vb.x, vb.y), fmaxf(vb.z, vb.w));
+      const float mc = fmaxf(fmaxf(vc.x, vc.y), fmaxf(vc.z, vc.w));
+      const float cm = fmaxf(ma, fmaxf(mb, mc));
+      kmin = fminf(kmin, fminf(fminf(fminf(va.x, va.y), fminf(va.z, va.w)),
+                               fminf(fminf(fminf(vb.x, vb.y), fminf(vb.z, vb.w)), fminf(fminf(vc.x, vc.y), fminf(vc.z, vc.w)))));
+      if (cm > tm) {                                         // rare after the first pieces
+        ts *= f_ex2((tm - cm) * c2);
+        tm = cm;
+        ntc = -cm * c2;
+        const float4 vv = (ma == cm) ? va : (mb == cm) ? vb : vc;
+        const int bb = 4 * ((ma == cm) ? ca : (mb == cm) ? cb : cc) - mis;
+        ti = (vv.x == cm) ? bb : (vv.y == cm) ? bb + 1 : (vv.z == cm) ? bb + 2 : bb + 3;
+      }
+      const float sa = (f_ex2(fmaf(va.x, c2, ntc)) + f_ex2(fmaf(va.y, c2, ntc))) + (f_ex2(fmaf(va.z, c2, ntc)) + f_ex2(fmaf(va.w, c2, ntc)));
+      const float sb = (f_ex2(fmaf(vb.x, c2, ntc)) + f_ex2(fmaf(vb.y, c2, ntc))) + (f_ex2(fmaf(vb.z, c2, ntc)) + f_ex2(fmaf(vb.w, c2, ntc)));
+      const float sc3 = (f_ex2(fmaf(vc.x, c2, ntc)) + f_ex2(fmaf(vc.y, c2, ntc))) + (f_ex2(fmaf(vc.z, c2, ntc)) + f_ex2(fmaf(vc.w, c2, ntc)));
+      ts += (sa + sb) + sc3;
+    };
+#if NSF_STREAM
+    // interior chunks 1 .. W4-2 straight from global memory, three 128-bit loads in flight per thread
+    for (int ca = 1 + tid; ca < 1 + NI; ca += 3 * FT) {
+      const int cb = ca + FT, cc = cb + FT;
+      if (cc < 1 + NI) {
+        const float4 va = raw4_l(ca), vb = raw4_l(cb), vc = raw4_l(cc);
+        online12(va, vb, vc, ca, cb, cc);
+      } else {
+        online4(raw4_l(ca), 4 * ca - mis);
+        if (cb < 1 + NI) online4(raw4_l(cb), 4 * cb - mis);
+      }
+    }
+#else
     for (int k = 0; k < F_PIECES; ++k) {
       const int c0 = 1 + k * PC;
       int c1 = c0 + PC;
@@ -310,38 +421,22 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       const int ca = c0 + tid, cb = ca + FT, cc = cb + FT;
       if (cc < c1) {
         const float4 va = w4[ca], vb = w4[cb], vc = w4[cc];
-        const float ma = fmaxf(fmaxf(va.x, va.y), fmaxf(va.z, va.w));
-        const float mb = fmaxf(fmaxf(vb.x, vb.y), fmaxf(vb.z, vb.w));
-        const float mc = fmaxf(fmaxf(vc.x, vc.y), fmaxf(vc.z, vc.w));
-        const float cm = fmaxf(ma, fmaxf(mb, mc));
-        kmin = fminf(kmin, fminf(fminf(fminf(va.x, va.y), fminf(va.z, va.w)),
-                                 fminf(fminf(fminf(vb.x, vb.y), fminf(vb.z, vb.w)), fminf(fminf(vc.x, vc.y), fminf(vc.z, vc.w)))));
-        if (cm > tm) {                                       // rare after the first pieces
-          ts *= f_ex2((tm - cm) * c2);
-          tm = cm;
-          ntc = -cm * c2;
-          const float4 vv = (ma == cm) ? va : (mb == cm) ? vb : vc;
-          const int bb = 4 * ((ma == cm) ? ca : (mb == cm) ? cb : cc) - mis;
-          ti = (vv.x == cm) ? bb : (vv.y == cm) ? bb + 1 : (vv.z == cm) ? bb + 2 : bb + 3;
-        }
-        const float sa = (f_ex2(fmaf(va.x, c2, ntc)) + f_ex2(fmaf(va.y, c2, ntc))) + (f_ex2(fmaf(va.z, c2, ntc)) + f_ex2(fmaf(va.w, c2, ntc)));
-        const float sb = (f_ex2(fmaf(vb.x, c2, ntc)) + f_ex2(fmaf(vb.y, c2, ntc))) + (f_ex2(fmaf(vb.z, c2, ntc)) + f_ex2(fmaf(vb.w, c2, ntc)));
-        const float sc3 = (f_ex2(fmaf(vc.x, c2, ntc)) + f_ex2(fmaf(vc.y, c2, ntc))) + (f_ex2(fmaf(vc.z, c2, ntc)) + f_ex2(fmaf(vc.w, c2, ntc)));
-        ts += (sa + sb) + sc3;
+        online12(va, vb, vc, ca, cb, cc);
       } else {
         if (ca < c1) online4(w4[ca], 4 * ca - mis);
         if (cb < c1) online4(w4[cb], 4 * cb - mis);
       }
     }
+#endif
     pc.mark(1);                                            // L: waits + estimate over the pieces
     __syncthreads();                                       // edge chunks written by threads 0..7
     {
       const float keep = kmin;                             // the edge chunks carry -inf padding: not part of the range
-      if (tid == 0) online4(w4[0], -mis);
-      if (tid == 32) online4(w4[W4 - 1], 4 * (W4 - 1) - mis);
+      if (tid == 0) online4(raw4_l(0), -mis);
+      if (tid == 32) online4(raw4_l(W4 - 1), 4 * (W4 - 1) - mis);
       kmin = keep;
       if (tid == 0 || tid == 32) {
-        const float4 v = tid == 0 ? w4[0] : w4[W4 - 1];
+        const float4 v = tid == 0 ? raw4_l(0) : raw4_l(W4 - 1);
         if (v.x > -INFINITY) kmin = fminf(kmin, v.x);
         if (v.y > -INFINITY) kmin = fminf(kmin, v.y);
         if (v.z > -INFINITY) kmin = fminf(kmin, v.z);
@@ -361,8 +456,13 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       for (int k = 0; k < 2; ++k) {
         const int id = P.mask_id[k];
         if (id >= 0 && id < V) {
+#if NSF_STREAM
+          const float x = g[id];
+          if (x > -INFINITY) ssum -= f_ex2((x - M) * c2);
+#else
           const float x = words[id + mis];
           if (x > -INFINITY) { ssum -= f_ex2((x - M) * c2); words[id + mis] = -INFINITY; }
+#endif
           if (id == top_id) remax = 1;
         }
       }
@@ -373,7 +473,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     if (sc->remax) {                                       // rare: the row maximum itself was forbidden
       u64 pm = 0;
       for (int c = tid; c < W4; c += FT) {
-        const float4 v = w4[c];
+        const float4 v = raw4_p(c);
         const int b = 4 * c - mis;
         u64 p;
         p = pack_of(v.x + 0.0f, b); pm = p > pm ? p : pm;
@@ -386,7 +486,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       top_id = id_of_pack(pm);
       float s = 0.f;
       for (int c = tid; c < W4; c += FT) {
-        const float4 v = w4[c];
+        const float4 v = raw4_p(c);
         s += f_ex2((v.x - M) * c2) + f_ex2((v.y - M) * c2) + f_ex2((v.z - M) * c2) + f_ex2((v.w - M) * c2);
       }
       s = f_sum_f(s, sc->red);
@@ -439,7 +539,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     int cnt_hi = 0;
     const bool need_count = P.topk < V;                      // otherwise only "at least 2 kept" matters
     for (int c = tid; c < W4; c += FT) {
-      const float4 v = w4[c];
+      const float4 v = raw4_p(c);
       const int b = 4 * c - mis;
       const double e0 = ns_exp64_core(a_of(v.x), tab);
       const double e1 = ns_exp64_core(a_of(v.y), tab);
@@ -458,7 +558,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       o.y = h1 ? f_pack_e(e1) : 0.0f;
       o.z = h2 ? f_pack_e(e2) : 0.0f;
       o.w = h3 ? f_pack_e(e3) : 0.0f;
-      w4[c] = o;
+      word_st4(c, o);
       if (!((h0 | l0) & (h1 | l1) & (h2 | l2) & (h3 | l3))) {   // rare: inside the guard band
         if (!(h0 | l0)) band_push(b, e0);
         if (!(h1 | l1)) band_push(b + 1, e1);
@@ -546,8 +646,8 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       }
     };
     for (int c = tid; c < W4; c += 2 * FT) {
-      const float4 v = w4[c];
-      const float4 w = (c + FT < W4) ? w4[c + FT] : make_float4(0.f, 0.f, 0.f, 0.f);   // e32 == 0: no-op
+      const float4 v = word_ld4(c);
+      const float4 w = (c + FT < W4) ? word_ld4(c + FT) : make_float4(0.f, 0.f, 0.f, 0.f);   // packed 0: no-op
       const int b = 4 * c - mis;
       uint32_t q[8];
       bool k[8];
@@ -573,7 +673,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     if (nu > F_U_CAP) { if (tid == 0) hand_over(P, slow_ws, row, F_WHY_ULIST); return; }
     for (int u = tid; u < nu; u += FT) {
       const int id = ulist[u];
-      atomicAdd(&hist[bin_of_e(words[id + mis])], exact_mass(id));
+      atomicAdd(&hist[bin_of_e(word_ld1(id + mis))], exact_mass(id));
     }
     if (tid < nband && band[tid].kept) {
       const double e = band[tid].e;
@@ -652,9 +752,9 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       // three float4 per iteration: the loads and the twelve bucket tests overlap, matches are rare
       for (int c = tid; c < W4; c += 3 * FT) {
         const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 va = w4[c];
-        const float4 vb = (c + FT < W4) ? w4[c + FT] : zero;
-        const float4 vc = (c + 2 * FT < W4) ? w4[c + 2 * FT] : zero;
+        const float4 va = word_ld4(c);
+        const float4 vb = (c + FT < W4) ? word_ld4(c + FT) : zero;
+        const float4 vc = (c + 2 * FT < W4) ? word_ld4(c + 2 * FT) : zero;
         const bool ha = hit4(va), hb = hit4(vb), hc = hit4(vc);
         if (ha | hb | hc) {
           if (ha) gather4(va, c);
@@ -728,7 +828,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       int j; u64 bj, wj;
       if (select_tau(R, &j, &bj, &wj)) {
         truncated = true;
-        trunc_e.ebits = __float_as_uint(words[j + mis]);
+        trunc_e.ebits = __float_as_uint(word_ld1(j + mis));
         for (int k = 0; k < nband; ++k) if (band[k].id == j) trunc_e.ebits = __float_as_uint(f_pack_e(band[k].e));
         trunc_e.id = j; trunc_e.key = g[j] + 0.0f;
         slack = R - bj;
@@ -763,7 +863,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       int tok = meta.tok;
       if (tok < 0 || tok >= V) tok = top_id;
       // is the observed token in the kept set, and in which bucket?
-      float e32t = words[tok + mis];
+      float e32t = word_ld1(tok + mis);
       if (__float_as_uint(e32t) == 0u) {
         for (int k = 0; k < nband; ++k)
           if (band[k].id == tok && band[k].kept) e32t = f_pack_e(band[k].e);
@@ -796,7 +896,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
 }
 
 template <bool UNIT_TEMP, int MODE>
-__global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t* slow_ws) {
+__global__ void __launch_bounds__(FT, NSF_MIN_CTAS) ac_fast_kernel(ns_ac_params P, int32_t* slow_ws) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FastSmem sm;
   sm.tab = reinterpret_cast<double*>(smem_raw);
@@ -805,14 +905,20 @@ __global__ void __launch_bounds__(FT, 1) ac_fast_kernel(ns_ac_params P, int32_t*
   sm.ulist = reinterpret_cast<int*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16);
   sm.clist = reinterpret_cast<CandEntry*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16 + F_U_CAP * 4);
   sm.sc = reinterpret_cast<FScal*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16 + F_U_CAP * 4 + 2 * F_C_CAP * 16);
+#if NSF_STREAM
+  sm.words = reinterpret_cast<float*>(reinterpret_cast<char*>(P.scratch) + (size_t)blockIdx.x * (size_t)P.scratch_stride);
+#else
   sm.words = reinterpret_cast<float*>(smem_raw + FIXED_BYTES);   // element id lives at words[id + mis]
+#endif
   const int tid = threadIdx.x;
   constexpr int HELPER = FT - 32;                          // lane that fetches the next row's scalars
   for (int i = tid; i < NS_EXP_N; i += FT) sm.tab[i] = c_exp_tab[i];
+#if !NSF_STREAM
   if (tid == 0) {
     for (int k = 0; k < F_PIECES; ++k) f_mbar_init(&sm.sc->bar[k], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+#endif
   if (tid == HELPER && (int)blockIdx.x < P.B) sm.sc->meta[0] = f_load_meta(P, blockIdx.x, MODE);
   uint32_t parity = 0;                                     // bit k: phase parity of piece k's mbarrier
   PhaseClock pc;
