@@ -172,6 +172,8 @@ typedef struct ns_codec_params {
   const int32_t* total_bits; /* rank decode: payload bit count (state["residual_bits"], arithmetic.py:167) */
   uint8_t* nbits_out;       /* bits consumed / emitted this step; may be NULL */
   const int32_t* lut;       /* bins: word -> bin [V] (get_bins, block_baseline.py:9-24) */
+  double top_p;             /* rank: quality top_p (quality.py:85-91), used when 0 < top_p < 1; else none */
+  double min_prob;          /* rank: quality min_prob (quality.py:93-96), used when > 0; else none */
 } ns_codec_params;
 
 int ns_sizeof_codec_params(void);

@@ -66,6 +66,7 @@ class CodecParams(C.Structure):
         ("token_in", C.c_void_p),
         ("out_bits", C.c_void_p), ("out_stride", C.c_int64), ("out_len", C.c_void_p),
         ("total_bits", C.c_void_p), ("nbits_out", C.c_void_p), ("lut", C.c_void_p),
+        ("top_p", C.c_double), ("min_prob", C.c_double),
     ]
 
 

@@ -44,7 +44,9 @@ class CodecStreams:
     """B streams of one comparison codec.  ``kind`` in {"rank", "huffman", "bins"}."""
 
     def __init__(self, kind: str, batch: int, vocab: int, *, param: int = 0, temp: float = 1.0,
-                 topk: int = 0, device="cuda", token_cap: int = 1024, mask_ids: Optional[Sequence[int]] = None):
+                 topk: int = 0, top_p: Optional[float] = None, min_prob: Optional[float] = None,
+                 cap_per_token_bits: Optional[int] = None, device="cuda", token_cap: int = 1024,
+                 mask_ids: Optional[Sequence[int]] = None):
         if kind not in ("rank", "huffman", "bins"):
             raise ValueError("unknown codec kind: %s" % kind)
         self.lib = N.load()
@@ -52,6 +54,22 @@ class CodecStreams:
             raise N.NativeLibraryError("no CUDA device: the codecs have no CPU fallback")
         self.kind, self.B, self.V = kind, int(batch), int(vocab)
         self.param, self.temp, self.topk = int(param), float(temp), int(topk)
+        # rank codec quality filters (codec/quality.py:57-105), evaluated on chip
+        if top_p is not None and not 0.0 < float(top_p) <= 1.0:
+            raise ValueError("top_p must be within (0, 1]")                      # quality.py:86-87
+        if min_prob is not None and float(min_prob) < 0.0:
+            raise ValueError("min_prob must be non-negative")                    # quality.py:94-95
+        if cap_per_token_bits is not None and int(cap_per_token_bits) <= 0:
+            raise ValueError("cap_per_token_bits must be positive")              # quality.py:121-122
+        if (top_p is not None or min_prob is not None or cap_per_token_bits is not None) and kind != "rank":
+            raise ValueError("quality filters belong to the rank codec")
+        # top_p == 1 cuts wherever the reference's running sum happens to round to >= 1: treated as "no cut"
+        self.top_p = float(top_p) if top_p is not None and float(top_p) < 1.0 else 0.0
+        self.min_prob = float(min_prob) if min_prob is not None else 0.0
+        # cap_per_token_bits sharpens the probabilities by a temperature (quality.py:108-141): the order and
+        # the support of the distribution -- all the rank codec reads -- do not change (pinned by the
+        # rank_v2048_cap3 golden), so the key is accepted and needs no device work
+        self.cap_per_token_bits = cap_per_token_bits
         self.device = torch.device(device)
         if mask_ids is None:
             # the baselines forbid the same two tokens as the arithmetic coder; the rank codec none
@@ -112,6 +130,7 @@ class CodecStreams:
         else:
             p.logits = None; p.ld = self.V
         p.B = self.B; p.V = self.V; p.temp = self.temp; p.param = self.param; p.topk = self.topk
+        p.top_p = self.top_p; p.min_prob = self.min_prob
         p.mask_id[0], p.mask_id[1] = self.mask_ids[0], self.mask_ids[1]
         p.phase = self.phase.data_ptr(); p.status = self.status.data_ptr()
         p.ntok = self.ntok.data_ptr(); p.token_cap = self.token_cap; p.ntok_total = N.ptr(self.ntok_total)

@@ -177,6 +177,71 @@ __global__ void __launch_bounds__(NT, 1) rank_kernel(ns_codec_params P) {
   for (int i = tid; i < V; i += NT) cnt += (((double)keys[i] / P.temp - dm) >= -745.0) ? 1 : 0;
   u64 n_pos = block_reduce_u(cnt, OpAddU(), sm.sc->red);
   if (P.topk > 0 && n_pos > (u64)P.topk) n_pos = (u64)P.topk;          // quality.py:76-81
+  // top_p / min_prob (quality.py:85-96): both keep a prefix of the order, judged on the unfiltered fp64
+  // softmax; the renormalisation (:101-103) changes neither the order nor the support
+  const bool use_p = P.top_p > 0.0 && P.top_p < 1.0, use_min = P.min_prob > 0.0;
+  if (use_p || use_min) {
+    double* tab = reinterpret_cast<double*>(sm.raw);
+    for (int i = tid; i < NS_EXP_N; i += NT) tab[i] = c_exp_tab[i];
+    __syncthreads();
+    const double temp = P.temp;
+    auto e_of = [&](float k) -> double { return ns_exp64_neg((double)k / temp - dm, tab); };
+    double acc = 0.0;
+    for (int i = tid; i < V; i += NT) acc += e_of(keys[i]);
+    const double inv = 1.0 / block_sum_d(acc, sm.sc->red);              // softmax normaliser, lm/arithmetic.py:73
+    if (use_min) {
+      u64 c = 0;
+      for (int i = tid; i < V; i += NT) c += (e_of(keys[i]) * inv >= P.min_prob) ? 1 : 0;
+      const u64 n_min = block_reduce_u(c, OpAddU(), sm.sc->red);
+      if (n_min < n_pos) n_pos = n_min;                                 // 0 -> QualityConfigError :98-99, flagged below
+    }
+    if (use_p) {
+      // cutoff = #(positions whose running sum stays below top_p) (:89-90): masses as 2^-62 fixed point (order-free
+      // sums), a mass histogram over 1024 monotone key buckets, exact resolution inside the bucket
+      constexpr int NB64 = HIST_BYTES / 8;
+      u64* h64 = reinterpret_cast<u64*>(sm.hist);
+      const double two62 = 4611686018427387904.0;
+      const double f_top = ceil(P.top_p * two62);
+      const u64 tau = f_top >= 1.0 ? (u64)f_top - 1ull : 0ull;          // first position with sum >= top_p
+      const float span = m - key_of_pack(pmin);
+      const float scale = span > 0.0f ? (float)NB64 / span : 0.0f;
+      __syncthreads();
+      for (int i = tid; i < NB64; i += NT) h64[i] = 0ull;
+      if (tid == 0) sm.sc->list_count = 0;
+      __syncthreads();
+      for (int i = tid; i < V; i += NT) {
+        const float k = keys[i];
+        const u64 f = __double2ull_rz(e_of(k) * inv * two62);
+        if (f) atomicAdd(&h64[bin_of(k, m, scale, NB64)], f);
+      }
+      __syncthreads();
+      sel_locate<u64, NB64>(h64, tau, sm.sc);
+      const int tb = sm.sc->sel_bin;
+      const u64 prefix = sm.sc->sel_prefix;
+      if (tb >= 0) {                                                    // else the sum never reaches top_p: keep all
+        for (int i = tid; i < V; i += NT) {
+          const float k = keys[i];
+          if (bin_of(k, m, scale, NB64) == tb) {
+            const u64 f = __double2ull_rz(e_of(k) * inv * two62);
+            const int s = atomicAdd(&sm.sc->list_count, 1);
+            if (s < CODEC_LIST_CAP) { sm.list[s].pack = pack_of(k, i); sm.list[s].w = f; }
+          }
+        }
+        __syncthreads();
+        int n = sm.sc->list_count;
+        if (n > CODEC_LIST_CAP) { n = CODEC_LIST_CAP; if (tid == 0 && P.status) atomicOr(&P.status[row], NS_ST_BIN_OVERFLOW); }
+        sel_resolve(sm.list, n, tau, prefix, sm.sc);
+        if (sm.sc->res_found) {
+          const u64 tp = pack_of(keys[sm.sc->res_idx], sm.sc->res_idx);
+          u64 before = 0;
+          for (int i = tid; i < V; i += NT) before += pack_of(keys[i], i) > tp ? 1 : 0;
+          const u64 n_p = block_reduce_u(before, OpAddU(), sm.sc->red) + 1ull;   // order[:cutoff + 1], :91
+          if (n_p < n_pos) n_pos = n_p;
+        }
+      }
+      __syncthreads();
+    }
+  }
   int capacity = 0;
   while ((2ull << capacity) <= n_pos) ++capacity;                       // floor(log2(n_pos)), :379
   if (capacity <= 0) {                                                  // ArithmeticRangeError :149

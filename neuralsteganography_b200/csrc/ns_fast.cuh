@@ -401,14 +401,14 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     };
 #if NSF_STREAM
     // interior chunks 1 .. W4-2 straight from global memory, three 128-bit loads in flight per thread
-    for (int ca = 1 + tid; ca < 1 + NI; ca += 3 * FT) {
-      const int cb = ca + FT, cc = cb + FT;
-      if (cc < 1 + NI) {
-        const float4 va = raw4_l(ca), vb = raw4_l(cb), vc = raw4_l(cc);
+    for (int ca = 1 + tid; ca < 1 + NI; ca += 6 * FT) {
+      const int cb = ca + FT, cc = cb + FT, cd = cc + FT, ce = cd + FT, cf = ce + FT;
+      if (cf < 1 + NI) {
+        const float4 va = raw4_l(ca), vb = raw4_l(cb), vc = raw4_l(cc), vd = raw4_l(cd), ve = raw4_l(ce), vf = raw4_l(cf);
         online12(va, vb, vc, ca, cb, cc);
+        online12(vd, ve, vf, cd, ce, cf);
       } else {
-        online4(raw4_l(ca), 4 * ca - mis);
-        if (cb < 1 + NI) online4(raw4_l(cb), 4 * cb - mis);
+        for (int c = ca; c < 1 + NI; c += FT) online4(raw4_l(c), 4 * c - mis);
       }
     }
 #else
@@ -538,8 +538,16 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     double accl0 = 0.0, accl1 = 0.0, accl2 = 0.0, accl3 = 0.0;
     int cnt_hi = 0;
     const bool need_count = P.topk < V;                      // otherwise only "at least 2 kept" matters
+#if NSF_STREAM
+    float4 v_next = (tid < W4) ? raw4_p(tid) : make_float4(0.f, 0.f, 0.f, 0.f);
+#endif
     for (int c = tid; c < W4; c += FT) {
+#if NSF_STREAM
+      const float4 v = v_next;                               // loaded one iteration ahead (L2 latency)
+      if (c + FT < W4) v_next = raw4_p(c + FT);
+#else
       const float4 v = raw4_p(c);
+#endif
       const int b = 4 * c - mis;
       const double e0 = ns_exp64_core(a_of(v.x), tab);
       const double e1 = ns_exp64_core(a_of(v.y), tab);

@@ -42,18 +42,61 @@ def bits_to_bytes_msb(bits: Sequence[int]) -> bytes:
     return bytes(out)
 
 
-def rank_distribution(row: np.ndarray, temperature: float, top_k=None) -> np.ndarray:
-    """fp64 softmax of logits/temperature (lm/arithmetic.py:69-73) + top-k filter (quality.py:76-105)."""
+def rank_distribution(row: np.ndarray, temperature: float, top_k=None, top_p=None, min_prob=None,
+                      cap_per_token_bits=None) -> np.ndarray:
+    """fp64 softmax of logits/temperature (lm/arithmetic.py:69-73) + the quality filters of
+    codec/quality.py:57-105 (top_k, top_p, min_prob: each a prefix of the descending order, evaluated on
+    the unfiltered probabilities, then one renormalisation) + the entropy cap of :108-141."""
     x = row.astype(np.float64) / float(temperature)
     e = np.exp(x - x.max())
     p = e / e.sum()
-    if top_k is not None and top_k < p.size:
+    if top_k is not None or top_p is not None or min_prob is not None:
         order = np.argsort(-p, kind="stable")
-        keep = np.zeros(p.size, dtype=bool)
-        keep[order[: int(top_k)]] = True
+        keep = np.ones(p.size, dtype=bool)
+        if top_k is not None:                                           # :76-81
+            keep[:] = False
+            keep[order[: min(int(top_k), p.size)]] = True
+        if top_p is not None:                                           # :85-91
+            cutoff = int(np.searchsorted(np.cumsum(p[order]), top_p, side="left"))
+            inside = np.zeros(p.size, dtype=bool)
+            inside[order[: cutoff + 1]] = True
+            keep &= inside
+        if min_prob is not None:                                        # :93-96
+            keep &= p >= min_prob
+        if not keep.any():
+            raise ValueError("Quality policies removed all probability mass")   # :98-99
         f = np.where(keep, p, 0.0)
         p = f / f.sum()
+    if cap_per_token_bits is not None:
+        p = cap_bits(p, int(cap_per_token_bits))
     return p
+
+
+def _entropy_bits(p: np.ndarray) -> float:
+    v = p[p > 0.0]
+    return float(-(v * np.log2(v)).sum()) if v.size else 0.0
+
+
+def cap_bits(p: np.ndarray, cap: int) -> np.ndarray:
+    """cap_bits_per_token (quality.py:108-141): 60-step bisection on a sharpening temperature.  For the rank
+    codec only the support and the order of the result matter; both are unchanged unless the sharpening
+    underflows the tail or resurrects filtered tokens through the ``+1e-12`` (then the reference's order among
+    the equal probabilities is its unstable argsort's -- unpinned)."""
+    p = p / p.sum()
+    if _entropy_bits(p) <= cap:
+        return p
+    low, high, target = 1e-6, 1.0, p
+    for _ in range(60):
+        mid = (low + high) / 2.0
+        z = np.log(p + 1e-12) / mid
+        z -= z.max()
+        c = np.exp(z)
+        c = c / c.sum()
+        if _entropy_bits(c) > cap:
+            high = mid
+        else:
+            target, low = c, mid
+    return target
 
 
 def rank_tokens(p: np.ndarray) -> Tuple[np.ndarray, int]:
@@ -66,7 +109,7 @@ def rank_tokens(p: np.ndarray) -> Tuple[np.ndarray, int]:
     return order[: 1 << capacity], capacity
 
 
-def rank_encode(rows: Callable[[int], np.ndarray], payload: bytes, *, temperature: float = 1.0, top_k=None):
+def rank_encode(rows: Callable[[int], np.ndarray], payload: bytes, *, temperature: float = 1.0, top_k=None, **quality):
     """encode_with_lm (codec/arithmetic.py:122-169). Returns (tokens, history, total_bits)."""
     bits = bytes_to_bits_msb(payload)
     total = len(bits)
@@ -74,7 +117,7 @@ def rank_encode(rows: Callable[[int], np.ndarray], payload: bytes, *, temperatur
     tokens: List[int] = []
     history: List[int] = []
     while pos < total:                                                  # :146
-        ranked, capacity = rank_tokens(rank_distribution(rows(t), temperature, top_k))
+        ranked, capacity = rank_tokens(rank_distribution(rows(t), temperature, top_k, **quality))
         if capacity <= 0:
             raise ValueError("no capacity")
         chunk = bits[pos: pos + capacity]
@@ -91,11 +134,11 @@ def rank_encode(rows: Callable[[int], np.ndarray], payload: bytes, *, temperatur
 
 
 def rank_decode(rows, tokens: Sequence[int], history: Sequence[int], total_bits: int, *,
-                temperature: float = 1.0, top_k=None) -> bytes:
+                temperature: float = 1.0, top_k=None, **quality) -> bytes:
     """decode_with_lm (codec/arithmetic.py:172-231)."""
     out: List[int] = []
     for t, tok in enumerate(tokens):
-        ranked, capacity = rank_tokens(rank_distribution(rows(t), temperature, top_k))
+        ranked, capacity = rank_tokens(rank_distribution(rows(t), temperature, top_k, **quality))
         index = int(np.nonzero(ranked == tok)[0][0])                    # :211
         emitted = [(index >> s) & 1 for s in reversed(range(capacity))]  # :529-530
         out += emitted[: history[t]]                                    # :216
@@ -237,7 +280,20 @@ CODEC_CASES = [
     dict(name="rank_v2048_t10", kind="rank", V=2048, T=24, scale=3.0, param=0, temperature=1.0, streams=4, bits=160),
     dict(name="rank_v42001_t08", kind="rank", V=42001, T=8, scale=2.5, param=0, temperature=0.8, streams=2, bits=240),
     dict(name="rank_v2048_topk64", kind="rank", V=2048, T=24, scale=3.0, param=64, temperature=1.0, streams=3, bits=160),
+    dict(name="rank_v2048_topp90", kind="rank", V=2048, T=24, scale=3.0, param=0, temperature=1.0, streams=3, bits=160,
+         top_p=0.9),
+    dict(name="rank_v2048_minp", kind="rank", V=2048, T=24, scale=3.0, param=0, temperature=1.0, streams=3, bits=160,
+         min_prob=2e-4),
+    dict(name="rank_v42001_mix", kind="rank", V=42001, T=8, scale=2.5, param=6000, temperature=0.8, streams=2, bits=200,
+         top_p=0.97, min_prob=1e-6),
+    dict(name="rank_v2048_cap3", kind="rank", V=2048, T=24, scale=3.0, param=0, temperature=1.0, streams=2, bits=160,
+         cap_per_token_bits=3),
 ]
+
+
+def rank_quality(cfg) -> dict:
+    """The quality keys of a rank case besides top_k (golden metadata -> oracle / kernel arguments)."""
+    return {k: cfg[k] for k in ("top_p", "min_prob", "cap_per_token_bits") if cfg.get(k) is not None}
 
 
 def make_codec_goldens(out_dir, logits_pool, message_bits, rows_for):
@@ -271,12 +327,15 @@ def make_codec_goldens(out_dir, logits_pool, message_bits, rows_for):
             else:
                 payload = bits_to_bytes_msb(msg.tolist())
                 top_k = cfg["param"] or None
-                quality = {"top_k": top_k} if top_k else None
+                extra = rank_quality(cfg)
+                quality = dict(extra, **({"top_k": top_k} if top_k else {})) or None
                 ref_tok, state = H.ref_rank_encode(rows, payload, temperature=cfg["temperature"], quality=quality)
                 ref_payload = H.ref_rank_decode(rows, ref_tok, state, temperature=cfg["temperature"], quality=quality)
-                tok, hist, total = rank_encode(rows, payload, temperature=cfg["temperature"], top_k=top_k)
-                back = rank_decode(rows, ref_tok, hist, total, temperature=cfg["temperature"], top_k=top_k)
+                tok, hist, total = rank_encode(rows, payload, temperature=cfg["temperature"], top_k=top_k, **extra)
+                back = rank_decode(rows, ref_tok, hist, total, temperature=cfg["temperature"], top_k=top_k, **extra)
                 assert tok == list(ref_tok), (cfg["name"], s)
+                if "cap_per_token_bits" in extra:      # the cap leaves order and support alone: same tokens without it
+                    assert tok == rank_encode(rows, payload, temperature=cfg["temperature"], top_k=top_k)[0]
                 assert tuple(hist) == tuple(state["history"]), (cfg["name"], s)
                 assert back == ref_payload == payload, (cfg["name"], s)
                 data["history_%d" % s] = np.asarray(hist, dtype=np.int32)

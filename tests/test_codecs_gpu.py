@@ -25,7 +25,8 @@ def test_codec_goldens_bit_exact(golden_dir, cases):
         want_bits = [data["decoded_%d" % s].tolist() for s in range(S)]
         if cfg["kind"] == "rank":
             payload_bits = [K.bytes_to_bits_msb(K.bits_to_bytes_msb(m)) for m in msgs]      # byte padded, MSB first
-            st = _codec("rank", S, cfg["V"], temp=cfg["temperature"], topk=cfg["param"], token_cap=128)
+            st = _codec("rank", S, cfg["V"], temp=cfg["temperature"], topk=cfg["param"], token_cap=128,
+                        **K.rank_quality(cfg))                     # top_p / min_prob / cap_per_token_bits cases
             st.set_messages(payload_bits)
             toks = st.encode(fn, poll_every=4)
             assert toks == want_tok, cfg["name"]
@@ -83,6 +84,45 @@ def test_codecs_at_config5_shape_roundtrip():
         rows = lambda t, r=r: pool2[t % T][r].cpu().numpy()
         want, hist, total = K.rank_encode(rows, K.bits_to_bytes_msb(pmsgs[r]), temperature=0.9)
         assert toks[r] == want, r
+
+
+def test_rank_quality_filters_at_config4_shape():
+    """top_k + top_p + min_prob on chip (codec/quality.py:57-105) at the gpt2-fa vocabulary vs the oracle."""
+    V, B, T = 42001, 64, 3
+    g = torch.Generator(device="cuda").manual_seed(9)
+    pool = [torch.randn(B, V, generator=g, device="cuda") * 2.5 for _ in range(T)]
+    fn = lambda t: pool[t % T]
+    msgs = [message_bits(5000 + r, 96).tolist() for r in range(B)]
+    for q in (dict(top_p=0.5), dict(min_prob=3e-5), dict(topk=3000, top_p=0.999, min_prob=1e-7), dict(top_p=0.3)):
+        st = _codec("rank", B, V, temp=0.9, token_cap=128, **q)
+        st.set_messages(msgs)
+        toks = st.encode(fn, poll_every=2, max_steps=128)
+        assert st.all_done(), q
+        status = st.status.cpu().numpy()
+        assert int((status & 2).sum()) == 0, q
+        # a row whose filtered set holds a single token has no capacity: ArithmeticRangeError in the reference
+        # (codec/arithmetic.py:149), NS_ST_OUT_OF_RANGE here
+        stuck = [r for r in range(B) if status[r] & 1]
+        assert len(stuck) < B // 2, q
+        st.set_tokens(toks, total_bits=[len(m) for m in msgs])
+        bits = st.decode(fn)
+        oq = {("top_k" if k == "topk" else k): v for k, v in q.items()}
+        for r in range(B):
+            rows = lambda t, r=r: pool[t % T][r].cpu().numpy()
+            if r in stuck:
+                if r in stuck[:3]:
+                    with pytest.raises(ValueError):
+                        K.rank_encode(rows, K.bits_to_bytes_msb(msgs[r]), temperature=0.9, **oq)
+                continue
+            assert bits[r] == msgs[r], (q, r)
+            if r in (0, 31, 63) or r < 4:
+                want, hist, total = K.rank_encode(rows, K.bits_to_bytes_msb(msgs[r]), temperature=0.9, **oq)
+                assert toks[r] == want, (q, r)
+    # min_prob above every probability: the reference raises QualityConfigError (quality.py:98-99)
+    st = _codec("rank", B, V, temp=0.9, token_cap=8, min_prob=0.9)
+    st.set_messages(msgs)
+    st.encode_step(fn(0))
+    assert bool(((st.status & 1) != 0).all().item())
 
 
 def test_get_bins_matches_reference_recipe():

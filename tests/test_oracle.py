@@ -85,10 +85,11 @@ def test_codec_oracles_match_reference_goldens(golden_dir, cases):
             else:
                 payload = K.bits_to_bytes_msb(msg)
                 top_k = cfg["param"] or None
-                tok, hist, total = K.rank_encode(rows, payload, temperature=cfg["temperature"], top_k=top_k)
+                extra = K.rank_quality(cfg)                     # top_p / min_prob / cap_per_token_bits cases
+                tok, hist, total = K.rank_encode(rows, payload, temperature=cfg["temperature"], top_k=top_k, **extra)
                 assert tok == want_tok
                 assert hist == data["history_%d" % s].tolist()
-                back = K.rank_decode(rows, tok, hist, total, temperature=cfg["temperature"], top_k=top_k)
+                back = K.rank_decode(rows, tok, hist, total, temperature=cfg["temperature"], top_k=top_k, **extra)
                 assert K.bytes_to_bits_msb(back) == want_bits
 
 
