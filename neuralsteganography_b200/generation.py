@@ -79,9 +79,19 @@ class StegoGenerator:
         self.trunk.reset()
         self.logits.copy_(self.trunk.prefill(contexts.contiguous()))
 
-    def encode(self, contexts: torch.Tensor, messages: Sequence[Sequence[int]], *, poll_every: int = 16) -> List[List[int]]:
+    def _room(self, contexts: torch.Tensor, max_tokens: Optional[int]) -> int:
+        """Token budget of a stream: what fits the KV buffer, or ``max_tokens`` once the trunk slides its window."""
+        room = self.max_len - min(int(contexts.shape[-1]), 1022) - 1
+        if self.trunk.ring:
+            return int(max_tokens) if max_tokens else max(room, 1)
+        if max_tokens and max_tokens > room:
+            raise ValueError("max_tokens=%d needs a KV buffer of at least 1023 slots (max_len >= 1023)" % max_tokens)
+        return int(max_tokens) if max_tokens else room
+
+    def encode(self, contexts: torch.Tensor, messages: Sequence[Sequence[int]], *, poll_every: int = 16,
+               max_tokens: Optional[int] = None) -> List[List[int]]:
         """Cover tokens for one message (list of 0/1) per stream."""
-        room = self.max_len - int(contexts.shape[-1]) - 1
+        room = self._room(contexts, max_tokens)
         coder = ArithmeticStreams(self.B, self.V, device=self.device, token_cap=max(1, room), **self.kw)
         coder.set_messages(messages)
         if self.collect_stats:

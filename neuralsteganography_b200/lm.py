@@ -217,9 +217,12 @@ class B200ArithmeticLM:
                 raise ConfigurationError("bit stream length must be a multiple of 8")
         ctx = self._check_context(context)
         gen = self._generator(len(bit_lists), q)
-        tokens = gen.encode(ctx, [list(map(int, b)) for b in bit_lists])
+        # with the sliding KV window (max_len >= 1023) the cover may outgrow the buffer: budget one token per bit
+        budget = max((len(b) for b in bit_lists), default=0) + 64 if gen.trunk.ring else None
+        tokens = gen.encode(ctx, [list(map(int, b)) for b in bit_lists], max_tokens=budget)
         if int((gen.coder.status & 8).sum().item()):
-            raise ConfigurationError("cover did not fit max_len=%d tokens; raise max_len or shorten the chunk" % self.max_len)
+            raise ConfigurationError("cover did not fit %d tokens; raise max_len (>= 1023 slides the window) or shorten "
+                                     "the chunk" % gen.coder.token_cap)
         return [[int(t) for t in row] for row in tokens]
 
     def decode_arithmetic_batch(self, token_lists: Sequence[Sequence[int]], context: Sequence[int], *,

@@ -8,8 +8,12 @@ with the coder step.  PyTorch is plumbing here (GEMMs via cuBLAS); the product i
 
 Position rule of the reference: the first call sees the whole context at positions
 0..L-1, later calls use ``past_len % n_positions`` (arithmetic.py:44-48); the context is
-cut to its last 1022 tokens (:90).  Streams longer than ``n_positions - 2`` would need the
-reference's sliding window (utils.py:19-30), which this trunk does not implement.
+cut to its last 1022 tokens (:90).  After every call the reference keeps the last 1022 cache
+entries (``limit_past``, utils.py:19-30): a token therefore attends to at most 1022 earlier
+entries plus itself, and once the cache is full every new token sits at position
+``1022 % n_positions``.  With buffers of at least 1023 slots the KV cache here is a ring of
+1023 slots (attention does not depend on the order of the keys), so streams of any length
+follow the same rule; shorter buffers only serve streams that end before they fill.
 """
 
 from __future__ import annotations
@@ -53,6 +57,8 @@ class StaticGPT2:
         self.v = torch.zeros_like(self.k)
         self.length = torch.zeros((), dtype=torch.long, device=self.device)   # tokens in the cache (same for all streams)
         self._arange_t = torch.arange(self.T, device=self.device)
+        self.window = 1022                                  # utils.py:19-30 (hard-coded in the reference)
+        self.ring = self.window + 1 if self.T >= self.window + 1 else 0   # ring slots; 0 = plain buffer
 
     # ------------------------------------------------------------------ context (variable length, eager)
     @torch.no_grad()
@@ -87,10 +93,15 @@ class StaticGPT2:
     def step(self, tokens: torch.Tensor) -> torch.Tensor:
         """Append ``tokens`` [B] (int64) at position ``length``; returns fp32 logits [B, V].  No host sync."""
         B = self.B
-        pos = self.length.remainder(self.n_positions).view(1)                        # arithmetic.py:44-48
+        if self.ring:
+            pos = self.length.clamp(max=self.window).remainder(self.n_positions).view(1)   # cache length, then :44-48
+            slot = self.length.remainder(self.ring).view(1)                          # overwrites the entry limit_past dropped
+            live = ((self._arange_t <= self.length) & (self._arange_t < self.ring))[None, None, None, :]
+        else:
+            pos = self.length.remainder(self.n_positions).view(1)                    # arithmetic.py:44-48
+            slot = self.length.clamp(max=self.T - 1).view(1)                         # device index: no host sync
+            live = (self._arange_t <= self.length)[None, None, None, :]              # keys 0..length
         x = self.wte.index_select(0, tokens) + self.wpe.index_select(0, pos)         # tensor indices: no host sync
-        slot = self.length.clamp(max=self.T - 1).view(1)                             # device index: no host sync
-        live = (self._arange_t <= self.length)[None, None, None, :]                  # keys 0..length
         for i, w in enumerate(self.layers):
             h = F.layer_norm(x, (self.n_embd,), w["ln1w"], w["ln1b"], self.eps)
             qkv = h @ w["qkvw"] + w["qkvb"]

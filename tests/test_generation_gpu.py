@@ -96,3 +96,30 @@ def test_provider_roundtrips_a_framed_packet():
     assert many[0] == many[1] == many[2]
     back = lm.decode_arithmetic_batch(many, ctx, quality=quality)
     assert all(bits_to_bytes_lsb(b) == pkt for b in back)
+
+
+def test_generation_slides_the_1022_token_window():
+    """a7: a stream that outgrows the KV window (context 1012 + 48 tokens) keeps coding under the CUDA graph:
+    ring cache + position rule of code_base/arithmetic.py:44-48 / utils.py:19-30; parity with the oracle on the
+    logits the windowed trunk produced, and the message comes back."""
+    from neuralsteganography_b200.generation import StegoGenerator
+    from neuralsteganography_b200.trunk import StaticGPT2
+    model = _small_model(vocab=2048, layers=2, width=64, heads=2)
+    B = 2
+    gen = StegoGenerator(model, B, max_len=1024, precision=16, temp=1.0, topk=2048, use_graph=True)
+    assert gen.trunk.ring == 1023
+    g = torch.Generator().manual_seed(11)
+    ctx = torch.randint(0, 2047, (1012,), generator=g)
+    msgs = [message_bits(70 + r, 400).tolist() for r in range(B)]
+    toks = gen.encode(ctx, msgs, poll_every=8, max_tokens=200)
+    assert gen.coder.all_done()
+    assert min(len(t) for t in toks) > 1023 - 1012                     # the window did slide
+    bits = gen.decode(ctx, toks, poll_every=8)
+    for r in range(B):
+        assert bits[r][: len(msgs[r])] == msgs[r], r
+    tr = StaticGPT2(model, 1, max_len=1024)
+    rows = [tr.prefill(ctx[None].cuda())[0].cpu().numpy()]
+    for t in toks[0][:-1]:
+        rows.append(tr.step(torch.tensor([t], device="cuda"))[0].cpu().numpy())
+    res = O.encode_stream(lambda t: rows[t], msgs[0], temp=1.0, precision=16, topk=2048, max_steps=len(rows))
+    assert res.tokens == toks[0]
