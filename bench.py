@@ -275,6 +275,33 @@ def run_gpu_arm(args):
     barrier()
     ems = e0.elapsed_time(e1)
 
+    # config 5: the comparison codecs at the same shape (rank 0; short legs, reported beside the headline)
+    codecs = None
+    if rank == 0 and not args.no_codecs:
+        from neuralsteganography_b200.codecs import CodecStreams
+        codecs = {}
+        cw, ck = 2, max(2, min(K, args.codec_steps))
+        for name, kind, kw in (("huffman_b3", "huffman", dict(param=3)), ("bins_b3", "bins", dict(param=3)),
+                               ("rank", "rank", dict())):
+            cs = CodecStreams(kind, B, V, token_cap=cw + ck + 2, device=dev, **kw)
+            cs.set_packed_messages(torch.from_numpy(words.view(np.int32)), torch.from_numpy(lens))
+            for t in range(cw):
+                cs.encode_step(pool[t % POOL])
+            torch.cuda.synchronize()
+            c0 = int(cs.cursor.sum().item())
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record()
+            for t in range(ck):
+                cs.encode_step(pool[(cw + t) % POOL])
+            k1.record()
+            torch.cuda.synchronize()
+            kms = k0.elapsed_time(k1)
+            ctps = B * ck / (kms * 1e-3)
+            codecs[name] = {"tokens_per_sec": ctps, "bits_per_token": (int(cs.cursor.sum().item()) - c0) / (B * ck),
+                            "roofline_frac": ctps * 4 * V / 1e9 / peaks()[0], "steps": ck,
+                            "flags": int((cs.status & 3).sum().item())}
+            del cs
+
     # final gather of the cover tokens (the only collective; outside the hot path)
     gather_ms = None
     if world > 1:
@@ -322,6 +349,7 @@ def run_gpu_arm(args):
                     "note": "host logits (pinned) -> H2D -> ns_ac_encode_step -> tokens D2H, per rank"},
             "gpu_launches": 2 * K,   # per step: ac_fast_kernel + ac_step_kernel draining the hand-over queue
             "gather_ms": gather_ms,
+            "codecs": codecs,
             "clocks": clocks,
         }
         print(json.dumps(line))
@@ -339,6 +367,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=400)
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--codec-steps", type=int, default=8)
+    ap.add_argument("--no-codecs", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -101,6 +101,14 @@ class CodecStreams:
         self.tokens.fill_(-1)
         self.phase.copy_(torch.where(self.msg_len > 0, 0, 2).to(torch.uint8))
 
+    def set_packed_messages(self, words_i32: torch.Tensor, lens_i32: torch.Tensor) -> None:
+        """Messages already packed MSB-first into 32-bit words [B, W] (+ bit counts [B]), host or device."""
+        self.msg = words_i32.to(self.device, non_blocking=True).contiguous()
+        self.msg_len = lens_i32.to(self.device, non_blocking=True).contiguous()
+        self.status.zero_(); self.ntok.zero_(); self.cursor.zero_()
+        self.tokens.fill_(-1)
+        self.phase.copy_(torch.where(self.msg_len > 0, 0, 2).to(torch.uint8))
+
     def set_tokens(self, token_lists: Sequence[Sequence[int]], total_bits: Optional[Sequence[int]] = None) -> None:
         lens = np.array([len(t) for t in token_lists], dtype=np.int32)
         cap = max(self.token_cap, int(lens.max()) if self.B else 1)

@@ -89,6 +89,33 @@ __global__ void k_f2f(unsigned long long* out, int iters, float a) {
   if (threadIdx.x == 0) out[blockIdx.x] = (unsigned long long)(t1 - t0) + (s == 12345.0f);
 }
 
+// 8 DFMA chains + NI independent integer multiply-adds per iteration: does the fp64 issue cost add to the
+// other instructions' (2 issue cycles per DFMA) or overlap with them?
+template <int NI>
+__global__ void k_mix(unsigned long long* out, int iters, double a, double b, uint32_t m) {
+  double v[8];
+  uint32_t u[NI > 0 ? NI : 1];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = a + j + threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < (NI > 0 ? NI : 1); ++j) u[j] = threadIdx.x + j;
+  long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __fma_rn(v[j], b, a);
+#pragma unroll
+    for (int j = 0; j < NI; ++j) u[j] = (u[j] ^ m) + (u[j] >> 3);
+  }
+  long long t1 = clock64();
+  double s = 0;
+  uint32_t x = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += v[j];
+#pragma unroll
+  for (int j = 0; j < (NI > 0 ? NI : 1); ++j) x += u[j];
+  if (threadIdx.x == 0) out[blockIdx.x] = (unsigned long long)(t1 - t0) + (s == 12345.0) + (x == 77u);
+}
+
 int main() {
   unsigned long long* d; cudaMalloc(&d, 148 * 8);
   unsigned long long h[148];
@@ -109,5 +136,9 @@ int main() {
   k_dfma<8><<<148, T>>>(d, it, 1.0, 0.999); report("DFMA 8 chains/thread", 8);
   k_mufu<4><<<148, T>>>(d, it, 0.5f); report("MUFU.EX2 (+FADD) 4 chains", 4);
   k_f2f<4><<<148, T>>>(d, it, 0.5f); report("F2F.F64.F32 + DMUL + F2F.F32.F64", 4);
+  k_mix<0><<<148, T>>>(d, it, 1.0, 0.999, 5u); report("8 DFMA + 0 int pairs", 8);
+  k_mix<4><<<148, T>>>(d, it, 1.0, 0.999, 5u); report("8 DFMA + 4 int pairs (8 instr)", 8);
+  k_mix<8><<<148, T>>>(d, it, 1.0, 0.999, 5u); report("8 DFMA + 8 int pairs (16 instr)", 8);
+  k_mix<16><<<148, T>>>(d, it, 1.0, 0.999, 5u); report("8 DFMA + 16 int pairs (32 instr)", 8);
   return 0;
 }
