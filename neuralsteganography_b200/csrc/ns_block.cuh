@@ -32,6 +32,7 @@ struct Scalars {
   u64 res_before;
   u64 res_w;
   int res_found;
+  u64 bar[8];            // mbarriers of the codecs' bulk row copy
 };
 
 constexpr int FIXED_BYTES = 26624;    // exp table, histogram, lists, scalars (both kernels); the row follows
