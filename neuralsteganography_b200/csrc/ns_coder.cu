@@ -544,16 +544,16 @@ int launch_exact(const ns_ac_params* p, u64* dbg_q, u64* dbg_meta, int32_t* slow
 }
 
 // fast kernel: persistent, one CTA per SM
-template <bool UNIT, int MODE>
+template <bool UNIT, int MODE, bool RANK>
 int launch_fast(const ns_ac_params* p, cudaStream_t st) {
   const int smem = FIXED_BYTES + (p->V + 8) * 4;
   static bool configured = false;
-  int rc = configure(nsf_smem::ac_fast_kernel<UNIT, MODE>, &configured);
+  int rc = configure(nsf_smem::ac_fast_kernel<UNIT, MODE, RANK>, &configured);
   if (rc != NS_OK) return rc;
   if (p->B == 0) return NS_OK;
   const int sms = num_sms();
   const int grid = p->B < sms ? p->B : sms;
-  nsf_smem::ac_fast_kernel<UNIT, MODE><<<grid, nsf_smem::FT, smem, st>>>(*p, p->slow_ws);
+  nsf_smem::ac_fast_kernel<UNIT, MODE, RANK><<<grid, nsf_smem::FT, smem, st>>>(*p, p->slow_ws);
   return check_launch();
 }
 
@@ -585,8 +585,11 @@ int dispatch(const ns_ac_params* p, u64* dbg_q, u64* dbg_meta, void* stream) {
     return launch_exact<MODE, uint32_t>(p, dbg_q, dbg_meta, p->slow_ws, st);
   }
   // throughput path: fast kernel, then the exact kernel on whatever it handed over
-  rc = (p->temp == 1.0) ? launch_fast<true, MODE == MODE_DEBUG ? MODE_ENC : MODE>(p, st)
-                        : launch_fast<false, MODE == MODE_DEBUG ? MODE_ENC : MODE>(p, st);
+  // (top-k small enough to bind and to fit the rank-form lists: the instantiation that carries that path)
+  constexpr int M2 = MODE == MODE_DEBUG ? MODE_ENC : MODE;
+  const bool rank = p->topk >= 2 && p->topk < p->V && p->topk <= nsf_smem::F_K_CAP;
+  if (rank) rc = (p->temp == 1.0) ? launch_fast<true, M2, true>(p, st) : launch_fast<false, M2, true>(p, st);
+  else rc = (p->temp == 1.0) ? launch_fast<true, M2, false>(p, st) : launch_fast<false, M2, false>(p, st);
   if (rc != NS_OK) return rc;
   return launch_exact<MODE, uint32_t>(p, dbg_q, dbg_meta, p->slow_ws, st);
 }

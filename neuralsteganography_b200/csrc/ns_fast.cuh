@@ -237,7 +237,217 @@ struct PhaseClock {
   __device__ __forceinline__ void mark(int k) { if (on) { const long long t = clock64(); acc[k] += (u64)(t - last); last = t; } }
 };
 
+
+#if !NSF_STREAM
+// ------------------------------------------------------------------------------------------------
+// Rank form of the cutoff (code_base/arithmetic.py:75 with top-k binding: k = topk because more than
+// topk tokens have p >= 1/range).  Only the topk largest logits matter, so no pass over the row touches
+// fp64: a count histogram of the keys that are certainly above the cutoff, the bucket of position
+// topk-1, a gather of the buckets before it (grouped by bucket, so ordering is local) plus an exact
+// resolution of the boundary bucket, then exp / bin widths / prefix sums for topk elements only.
+// Returns 0 when the row is not certainly in rank form (the caller goes on with the threshold form,
+// the histogram is clean again), 1 when the row is finished or handed over.
+// ------------------------------------------------------------------------------------------------
+constexpr int F_K_CAP = 512;         // topk the path holds (the candidate list area, one thread per kept token)
+constexpr int F_RB_CAP = 128;        // entries of the boundary bucket (the band list area)
+static_assert(F_K_CAP <= FT && F_K_CAP <= 2 * F_C_CAP && F_RB_CAP <= F_BAND_CAP, "rank-form capacities");
+static_assert(F_K_CAP * 16 <= F_NB * 4, "sorted arrays live in the histogram area");
+
 template <bool UNIT_TEMP, int MODE>
+__device__ __noinline__ int fast_rank_row(const ns_ac_params& P, int32_t* slow_ws, const int row,
+                                          const u64 m_lo, const u64 m_hi, const u64 m_window, const int m_slot,
+                                          const int m_cursor, const int m_mlen, const int m_tok,
+                                          uint32_t* hist, FScal* sc, CandEntry* top, BandEntry* bnd, const float* words,
+                                          const double* tab, const int mis, const int W4,
+                                          const float M, const int top_id, const float kappa_r,
+                                          const float clamp_key, const double dm) {
+  const float4* w4 = reinterpret_cast<const float4*>(words);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, K = P.topk;
+  const float span = M - kappa_r;
+  if (!(span > 0.0f)) return 0;
+  const float rscale = (float)F_NB / span;
+  // monotone bucket of a key without a conversion instruction: (M - v) * rscale, clamped, rounded by the
+  // 2^23 trick; the low mantissa bits are the bucket
+  const float b_off = M * rscale + 8388608.0f, b_max = 8388608.0f + (float)(F_NB - 1);
+  auto bucket = [&](float v) -> int {
+    return __float_as_int(fmaxf(fminf(fmaf(-v, rscale, b_off), b_max), 8388608.0f)) & (F_NB - 1);
+  };
+  // ---- pass A: count histogram of the keys certainly above the cutoff (padding and masks are -inf).
+  // Branch-free: keys below the cutoff add 0 to a bucket of the lane's own
+  auto count = [&](float v) {
+    const uint32_t inc = v >= kappa_r ? 1u : 0u;
+    atomicAdd(hist + (inc ? bucket(v) : (tid & (F_NB - 1))), inc);
+  };
+  for (int c = tid; c < W4; c += 2 * FT) {
+    const float4 v = w4[c];
+    const float4 w = (c + FT < W4) ? w4[c + FT] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    count(v.x); count(v.y); count(v.z); count(v.w);
+    count(w.x); count(w.y); count(w.z); count(w.w);
+  }
+  __syncthreads();
+  uint32_t hloc[F_BPT], tsum = 0;
+#pragma unroll
+  for (int b = 0; b < F_BPT; ++b) { hloc[b] = hist[tid * F_BPT + b]; tsum += hloc[b]; }
+  uint32_t inc = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) sc->red[warp] = inc;
+  if (tid == 0) { sc->sel_bin = -1; sc->sel_prefix = 0; }
+  __syncthreads();
+  uint32_t woff = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < FW; ++w) { const uint32_t x = (uint32_t)sc->red[w]; if (w < warp) woff += x; total += x; }
+  if (total <= (uint32_t)K) {                              // not certainly rank form: clean up, threshold form decides
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < F_BPT; ++b) hist[tid * F_BPT + b] = 0;
+    __syncthreads();
+    return 0;
+  }
+  // ---- bucket of position K-1; every bucket becomes (count | exclusive prefix << 16) for the gather
+  {
+    uint32_t excl = woff + inc - tsum;
+#pragma unroll
+    for (int b = 0; b < F_BPT; ++b) {
+      if (hloc[b] != 0 && excl <= (uint32_t)(K - 1) && (uint32_t)(K - 1) < excl + hloc[b]) { sc->sel_bin = tid * F_BPT + b; sc->sel_prefix = excl; }
+      hist[tid * F_BPT + b] = hloc[b] | ((excl < 0xffffu ? excl : 0xffffu) << 16);
+      excl += hloc[b];
+    }
+  }
+  __syncthreads();
+  const int tb = sc->sel_bin;
+  const int prefix = (int)sc->sel_prefix;                  // tokens in the buckets before tb: all kept
+  // ---- pass B: gather.  Buckets before tb land grouped by bucket at their prefix; tb goes to the boundary list
+  auto gather = [&](float v, int id) {
+    if (v >= kappa_r) {
+      const int b = bucket(v);
+      if (b < tb) {
+        const uint32_t old = atomicSub(&hist[b], 1u);        // low 16 bits: slots still free in the bucket
+        const uint32_t cnt_left = old & 0xffffu, ex = old >> 16;
+        CandEntry e; e.ebits = ex; e.id = id; e.w = 0u; e.key = v + 0.0f;
+        top[ex + cnt_left - 1u] = e;
+      } else if (b == tb) {
+        const int s2 = atomicAdd(&sc->u_n, 1);
+        if (s2 < F_RB_CAP) { bnd[s2].id = id; bnd[s2].kept = __float_as_int(v + 0.0f); }
+      }
+    }
+  };
+  // keys that can fall into buckets <= tb (a hair loose; `gather` decides exactly): rare, one branch per chunk
+  const float k_hit = M - ((float)tb + 1.5f) / rscale;
+  for (int c = tid; c < W4; c += 2 * FT) {
+    const float4 v = w4[c];
+    const float4 w = (c + FT < W4) ? w4[c + FT] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    const bool hv = (v.x >= k_hit) | (v.y >= k_hit) | (v.z >= k_hit) | (v.w >= k_hit);
+    const bool hw = (w.x >= k_hit) | (w.y >= k_hit) | (w.z >= k_hit) | (w.w >= k_hit);
+    if (hv | hw) {
+      if (hv) { const int id = 4 * c - mis; gather(v.x, id); gather(v.y, id + 1); gather(v.z, id + 2); gather(v.w, id + 3); }
+      if (hw) { const int id = 4 * (c + FT) - mis; gather(w.x, id); gather(w.y, id + 1); gather(w.z, id + 2); gather(w.w, id + 3); }
+    }
+  }
+  __syncthreads();
+  const int nbnd = sc->u_n;
+  if (nbnd > F_RB_CAP) { if (tid == 0) hand_over(P, slow_ws, row, F_WHY_BUCKET); return 1; }
+  auto before = [&](float ka, int ia, float kb, int ib) -> bool { return ka > kb || (ka == kb && ia < ib); };   // coder order
+  {   // boundary bucket: its first K - prefix tokens in coder order complete the kept set, already in order
+    const int need = K - prefix;
+    if (tid < nbnd) {
+      const float mk = __int_as_float(bnd[tid].kept);
+      const int mi = bnd[tid].id;
+      int r = 0;
+      for (int o = 0; o < nbnd; ++o) r += before(__int_as_float(bnd[o].kept), bnd[o].id, mk, mi) ? 1 : 0;
+      if (r < need) { CandEntry e; e.ebits = 0xffffffffu; e.id = mi; e.w = (uint32_t)(prefix + r); e.key = mk; top[prefix + r] = e; }
+    }
+  }
+  __syncthreads();
+  // ---- order inside each gathered bucket, exact e of the K kept tokens at their sorted positions
+  double* es = reinterpret_cast<double*>(hist);            // [F_K_CAP]
+  int* sid = reinterpret_cast<int*>(hist + 2 * F_K_CAP);   // [F_K_CAP]
+  int my_r = -1, my_id = 0;
+  float my_key = 0.0f;
+  if (tid < K) {
+    const CandEntry me = top[tid];
+    my_id = me.id; my_key = me.key;
+    if (me.ebits == 0xffffffffu) my_r = (int)me.w;         // boundary token: position known
+    else {
+      // its bucket occupies top[ex .. ex + n): n = distance to the next entry with another prefix
+      const int ex = (int)me.ebits;
+      int r = ex;
+      for (int o = ex; o < prefix && top[o].ebits == (uint32_t)ex; ++o) r += before(top[o].key, top[o].id, me.key, me.id) ? 1 : 0;
+      my_r = r;
+    }
+  }
+  __syncthreads();                                         // histogram words are free now
+  auto a_of = [&](float key) -> double {
+    double x = (double)fmaxf(key, clamp_key);
+    if (!UNIT_TEMP) x = __ddiv_rn(x, P.temp);
+    return x - dm;
+  };
+  if (tid < K) { es[my_r] = ns_exp64_core(a_of(my_key), tab); sid[my_r] = my_id; }
+  __syncthreads();
+  const double ev = tid < K ? es[tid] : 0.0;               // thread r holds the token of rank r
+  double S = ev, zero = 0.0;
+  u64 none = 0;
+  f_sum_ddu(S, zero, none, sc->red);                       // sum of the kept e, fixed order (:146)
+  const u64 lo = m_lo, R = m_hi - m_lo;
+  const double C = __ddiv_rn((double)R, S);
+  const u64 q = tid < K ? (u64)__double2ll_rn(ev * C) : 0ull;   // :146-149
+  u64 cum = q;                                             // inclusive prefix sums over the ranks (:150)
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const u64 t = __shfl_up_sync(0xffffffffu, cum, o); if (lane >= o) cum += t; }
+  __syncthreads();                                         // red of the sum is consumed
+  if (lane == 31) sc->red[warp] = cum;
+  __syncthreads();
+  u64 Q = 0;
+  {
+    u64 wo = 0;
+#pragma unroll
+    for (int w = 0; w < FW; ++w) { const u64 x = sc->red[w]; if (w < warp) wo += x; Q += x; }
+    cum += wo;
+  }
+  u64* cums = reinterpret_cast<u64*>(top);                 // [F_K_CAP]; the gathered list is no longer needed
+  if (tid < K) cums[tid] = cum;
+  if (tid == 0) { sc->res_idx = K; sc->res_found = 0; }
+  __syncthreads();
+  // ---- overfill (:153-158): drop the ranks from the first prefix sum above the range on
+  int kk = K;
+  u64 slack;
+  if (Q > R) {
+    if (tid < K && cum > R && (tid == 0 || cums[tid - 1] <= R)) sc->res_idx = tid;
+    __syncthreads();
+    kk = sc->res_idx;
+    slack = R - (kk > 0 ? cums[kk - 1] : 0ull);
+    __syncthreads();
+    if (tid == 0) sc->res_idx = K;
+    __syncthreads();
+  } else {
+    slack = R - Q;
+  }
+  // bin of rank r: [cums[r-1] + slack, cums[r] + slack), rank 0 starts at 0 and absorbs the slack (:158)
+  const u64 my_lo = (tid > 0 && tid < K) ? cums[tid - 1] + slack : 0ull;
+  const u64 my_hi = cum + slack;
+  if (MODE == MODE_ENC) {
+    const u64 m_rel = m_window - lo;                       // next `precision` message bits (:168-171)
+    if (tid < kk && my_lo <= m_rel && m_rel < my_hi) sc->res_idx = tid;   // :172 (empty bins never match)
+    __syncthreads();
+    const int r = sc->res_idx;
+    if (tid == (r < kk ? r : 0)) {
+      if (r >= kk && P.status) atomicOr(&P.status[row], NS_ST_BIN_OVERFLOW);     // cannot happen: the bins tile the range
+      finish_encode(P, row, m_slot, sid[tid], lo + my_lo, lo + my_hi, (u64)K, Q, m_cursor, m_mlen);   // :175-176
+    }
+  } else {
+    int tok = m_tok;
+    if (tok < 0 || tok >= P.V) tok = top_id;
+    if (tid < kk && sid[tid] == tok) { sc->res_idx = tid; sc->res_found = 1; }
+    __syncthreads();
+    const bool in_range = sc->res_found != 0;
+    const int r = in_range ? sc->res_idx : 0;              // :342 / :347-348: unknown tokens are coded as rank 0
+    if (tid == r) finish_decode(P, row, m_slot, in_range, lo + my_lo, lo + my_hi, (u64)K, Q);
+  }
+  return 1;
+}
+#endif
+
+template <bool UNIT_TEMP, int MODE, bool RANK>
 __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws, const int row, const RowMeta meta,
                                          const FastSmem sm, uint32_t& parity, PhaseClock& pc) {
   double* tab = sm.tab; uint32_t* hist = sm.hist; BandEntry* band = sm.band; int* ulist = sm.ulist;
@@ -532,6 +742,17 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       if (s < F_BAND_CAP) { band[s].id = id; band[s].kept = 0; band[s].e = e; }
     };
 
+#if !NSF_STREAM
+    if (RANK && P.topk < V && P.topk >= 2 && P.topk <= F_K_CAP) {
+      // top-k binds if more than topk tokens are above the cutoff even should the estimate be 2% off
+      const float kappa_r = kappa_hi + 0.02f * (float)temp;
+      if (fast_rank_row<UNIT_TEMP, MODE>(P, slow_ws, row, meta.lo, meta.hi, meta.window, meta.slot, meta.cursor, meta.mlen,
+                                        meta.tok, hist, sc, clist, band, words, tab, mis, W4, M, top_id, kappa_r, clamp_key, dm)) {
+        pc.mark(7);
+        return;
+      }
+    }
+#endif
     pc.mark(2);                                            // reductions, masks, row constants
     // ------------------------------------------------------------------ P1: the fp64 exp pass
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
@@ -903,8 +1124,10 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
   }
 }
 
-template <bool UNIT_TEMP, int MODE>
-__global__ void __launch_bounds__(FT, NSF_MIN_CTAS) ac_fast_kernel(ns_ac_params P, int32_t* slow_ws) {
+// RANK: compiled with the rank-form path (host picks it when 2 <= topk <= F_K_CAP and topk < V); the other
+// instantiation is the pure threshold-form kernel
+template <bool UNIT_TEMP, int MODE, bool RANK = false>
+__global__ void __launch_bounds__(FT, NSF_MIN_CTAS) ac_fast_kernel(const __grid_constant__ ns_ac_params P, int32_t* slow_ws) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FastSmem sm;
   sm.tab = reinterpret_cast<double*>(smem_raw);
@@ -943,7 +1166,7 @@ __global__ void __launch_bounds__(FT, NSF_MIN_CTAS) ac_fast_kernel(ns_ac_params 
     const int nrow = row + gridDim.x;
     const bool fetch = (tid == HELPER) && (nrow < P.B);
     if (fetch) next = f_load_meta(P, nrow, MODE);          // loads in flight while the row is processed
-    fast_row<UNIT_TEMP, MODE>(P, slow_ws, row, meta, sm, parity, pc);
+    fast_row<UNIT_TEMP, MODE, RANK>(P, slow_ws, row, meta, sm, parity, pc);
     if (fetch) sm.sc->meta[(it + 1) & 1] = next;
     if (pc.on) pc.acc[15] += 1;
   }

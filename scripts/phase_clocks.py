@@ -4,6 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from neuralsteganography_b200.coder import ArithmeticStreams
 V, B, P = 50257, int(os.environ.get("STREAMS", "4096")), 2
+TOPK, TEMP = int(os.environ.get("TOPK", str(V))), float(os.environ.get("TEMP", "1.0"))
 g = torch.Generator(device="cuda").manual_seed(1234)
 pool = [torch.randn(B, V, generator=g, device="cuda") * 3.0 for _ in range(P)]
 rng = np.random.default_rng(0)
@@ -12,12 +13,12 @@ names = ["prologue", "L wait+estimate", "reduce+consts", "P1 exp pass", "FIX", "
          "target sel", "epilogue", "row-top barrier", "  pro: entry+copy issue", "  pro: edge chunks", "  pro: hist zero",
          "  pro: L2 prefetch"]
 for mode in ("enc", "dec"):
-    st = ArithmeticStreams(B, V, precision=26, temp=1.0, topk=V, token_cap=32)
+    st = ArithmeticStreams(B, V, precision=26, temp=TEMP, topk=TOPK, token_cap=32)
     st.set_packed_messages(torch.from_numpy(words.view(np.int32)), torch.full((B,), 4096, dtype=torch.int32))
     for t in range(3): st.encode_step(pool[t % P])
     if mode == "dec":
         toks, n = st.tokens.clone(), st.ntok.clone()
-        st = ArithmeticStreams(B, V, precision=26, temp=1.0, topk=V, token_cap=32)
+        st = ArithmeticStreams(B, V, precision=26, temp=TEMP, topk=TOPK, token_cap=32)
         st.set_token_tensor(toks, n)
     st.prof = torch.zeros(32, dtype=torch.int64, device="cuda")
     step = st.encode_step if mode == "enc" else st.decode_step
