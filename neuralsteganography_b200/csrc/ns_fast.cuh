@@ -261,8 +261,14 @@ __device__ __noinline__ int fast_rank_row(const ns_ac_params& P, int32_t* slow_w
                                           const double* tab, const int mis, const int W4,
                                           const float M, const int top_id, const float kappa_r,
                                           const float clamp_key, const double dm) {
+  // the pointers come through a real call: tell the compiler they are shared-memory addresses (LDS / ATOMS,
+  // not generic loads and atomics)
+  __builtin_assume(__isShared(hist)); __builtin_assume(__isShared(sc)); __builtin_assume(__isShared(top));
+  __builtin_assume(__isShared(bnd)); __builtin_assume(__isShared(words)); __builtin_assume(__isShared(tab));
   const float4* w4 = reinterpret_cast<const float4*>(words);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, K = P.topk;
+  long long tq = clock64();                                // phase timers (slots 11..14, only with P.prof)
+  auto lap = [&](int k) { if (P.prof && tid == 0) { const long long t = clock64(); atomicAdd((unsigned long long*)&P.prof[k], (unsigned long long)(t - tq)); tq = t; } };
   const float span = M - kappa_r;
   if (!(span > 0.0f)) return 0;
   const float rscale = (float)F_NB / span;
@@ -285,6 +291,7 @@ __device__ __noinline__ int fast_rank_row(const ns_ac_params& P, int32_t* slow_w
     count(w.x); count(w.y); count(w.z); count(w.w);
   }
   __syncthreads();
+  lap(11);
   uint32_t hloc[F_BPT], tsum = 0;
 #pragma unroll
   for (int b = 0; b < F_BPT; ++b) { hloc[b] = hist[tid * F_BPT + b]; tsum += hloc[b]; }
@@ -317,6 +324,7 @@ __device__ __noinline__ int fast_rank_row(const ns_ac_params& P, int32_t* slow_w
   __syncthreads();
   const int tb = sc->sel_bin;
   const int prefix = (int)sc->sel_prefix;                  // tokens in the buckets before tb: all kept
+  lap(12);
   // ---- pass B: gather.  Buckets before tb land grouped by bucket at their prefix; tb goes to the boundary list
   auto gather = [&](float v, int id) {
     if (v >= kappa_r) {
@@ -332,19 +340,50 @@ __device__ __noinline__ int fast_rank_row(const ns_ac_params& P, int32_t* slow_w
       }
     }
   };
-  // keys that can fall into buckets <= tb (a hair loose; `gather` decides exactly): rare, one branch per chunk
+  // keys that can fall into buckets <= tb (a hair loose; `gather` decides exactly) are rare per element but
+  // present in almost every warp iteration, so the pass only lists their ids (a few predicated instructions per
+  // element); the listed tokens are then gathered one per thread.  The list borrows the exp table's words.
   const float k_hit = M - ((float)tb + 1.5f) / rscale;
-  for (int c = tid; c < W4; c += 2 * FT) {
+  int* cand = reinterpret_cast<int*>(const_cast<double*>(tab));
+  constexpr int CAND_CAP = NS_EXP_N * 2;
+  // first a branch-free sweep that only marks, per thread, the iterations whose eight keys hold a hit (one bit
+  // each); then every thread revisits its few marked iterations and lists the ids
+  uint32_t marks = 0;
+  {
+    int it = 0;
+    for (int c = tid; c < W4; c += 2 * FT, ++it) {
+      const float4 v = w4[c];
+      const float4 w = (c + FT < W4) ? w4[c + FT] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      const float mx = fmaxf(fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)), fmaxf(fmaxf(w.x, w.y), fmaxf(w.z, w.w)));
+      marks |= (mx >= k_hit ? 1u : 0u) << it;
+    }
+  }
+  auto note = [&](float v, int id) {
+    if (v >= k_hit) { const int s2 = atomicAdd(&sc->c_n, 1); if (s2 < CAND_CAP) cand[s2] = id; }
+  };
+  while (marks) {
+    const int it = __ffs(marks) - 1;
+    marks &= marks - 1u;
+    const int c = tid + it * 2 * FT;
     const float4 v = w4[c];
-    const float4 w = (c + FT < W4) ? w4[c + FT] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-    const bool hv = (v.x >= k_hit) | (v.y >= k_hit) | (v.z >= k_hit) | (v.w >= k_hit);
-    const bool hw = (w.x >= k_hit) | (w.y >= k_hit) | (w.z >= k_hit) | (w.w >= k_hit);
-    if (hv | hw) {
-      if (hv) { const int id = 4 * c - mis; gather(v.x, id); gather(v.y, id + 1); gather(v.z, id + 2); gather(v.w, id + 3); }
-      if (hw) { const int id = 4 * (c + FT) - mis; gather(w.x, id); gather(w.y, id + 1); gather(w.z, id + 2); gather(w.w, id + 3); }
+    const int id = 4 * c - mis;
+    note(v.x, id); note(v.y, id + 1); note(v.z, id + 2); note(v.w, id + 3);
+    if (c + FT < W4) {
+      const float4 w = w4[c + FT];
+      const int id2 = 4 * (c + FT) - mis;
+      note(w.x, id2); note(w.y, id2 + 1); note(w.z, id2 + 2); note(w.w, id2 + 3);
     }
   }
   __syncthreads();
+  const int ncand = sc->c_n;
+  if (ncand <= CAND_CAP) {
+    for (int j = tid; j < ncand; j += FT) { const int id = cand[j]; gather(words[id + mis], id); }
+  }
+  __syncthreads();
+  for (int i = tid; i < NS_EXP_N; i += FT) const_cast<double*>(tab)[i] = c_exp_tab[i];   // the table is back
+  if (ncand > CAND_CAP) { __syncthreads(); if (tid == 0) hand_over(P, slow_ws, row, F_WHY_BUCKET); return 1; }
+  __syncthreads();
+  lap(13);
   const int nbnd = sc->u_n;
   if (nbnd > F_RB_CAP) { if (tid == 0) hand_over(P, slow_ws, row, F_WHY_BUCKET); return 1; }
   auto before = [&](float ka, int ia, float kb, int ib) -> bool { return ka > kb || (ka == kb && ia < ib); };   // coder order
@@ -384,6 +423,7 @@ __device__ __noinline__ int fast_rank_row(const ns_ac_params& P, int32_t* slow_w
   };
   if (tid < K) { es[my_r] = ns_exp64_core(a_of(my_key), tab); sid[my_r] = my_id; }
   __syncthreads();
+  lap(14);
   const double ev = tid < K ? es[tid] : 0.0;               // thread r holds the token of rank r
   double S = ev, zero = 0.0;
   u64 none = 0;

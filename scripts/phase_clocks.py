@@ -10,8 +10,8 @@ pool = [torch.randn(B, V, generator=g, device="cuda") * 3.0 for _ in range(P)]
 rng = np.random.default_rng(0)
 words = rng.integers(0, 1 << 32, size=(B, 130), dtype=np.uint64).astype(np.uint32)
 names = ["prologue", "L wait+estimate", "reduce+consts", "P1 exp pass", "FIX", "P2 q pass", "fixups+scan", "overfill sel",
-         "target sel", "epilogue", "row-top barrier", "  pro: entry+copy issue", "  pro: edge chunks", "  pro: hist zero",
-         "  pro: L2 prefetch"]
+         "target sel", "epilogue", "row-top barrier", "  rank: histogram pass", "  rank: scan+locate", "  rank: list+gather",
+         "  rank: boundary+order+exp"]
 for mode in ("enc", "dec"):
     st = ArithmeticStreams(B, V, precision=26, temp=TEMP, topk=TOPK, token_cap=32)
     st.set_packed_messages(torch.from_numpy(words.view(np.int32)), torch.full((B,), 4096, dtype=torch.int32))
@@ -26,7 +26,7 @@ for mode in ("enc", "dec"):
     torch.cuda.synchronize()
     pr = st.prof.cpu().numpy().astype(np.float64)
     rows = pr[15]
-    print(mode, "rows", int(rows), "cycles/row total %.0f" % (pr[:15].sum() / rows))
+    print(mode, "rows", int(rows), "cycles/row total %.0f" % (pr[:11].sum() / rows))
     if pr[16:25].any():
         print("   piece arrival (cycles after row start, as seen by warp 1):", " ".join("%.0f" % (x / rows) for x in pr[16:25]))
     if pr[25:29].any():
@@ -34,4 +34,4 @@ for mode in ("enc", "dec"):
     for k, nm in enumerate(names):
         if k >= 11 and pr[k] == 0:
             continue
-        print("   %-18s %8.0f cyc/row %5.1f%%" % (nm, pr[k] / rows, 100 * pr[k] / pr[:15].sum()))
+        print("   %-18s %8.0f cyc/row %5.1f%%" % (nm, pr[k] / rows, 100 * pr[k] / pr[:11].sum()))
