@@ -302,6 +302,30 @@ def run_gpu_arm(args):
                             "flags": int((cs.status & 3).sum().item())}
             del cs
 
+    # config 2's coder settings (temp 0.9, precision 26, topk 300: the rank form of the cutoff) at the same shape
+    topk_leg = None
+    if rank == 0 and not args.no_codecs:
+        tk = ArithmeticStreams(B, V, precision=PRECISION, temp=0.9, topk=300, token_cap=K + W + 8, device=dev)
+        tk.set_packed_messages(torch.from_numpy(words.view(np.int32)), torch.from_numpy(lens))
+        tn = max(4, min(K, 4 * args.codec_steps))
+        for t in range(W):
+            tk.encode_step(pool[t % POOL])
+        torch.cuda.synchronize()
+        c0 = int(tk.cursor.sum().item())
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for t in range(tn):
+            tk.encode_step(pool[(W + t) % POOL])
+        k1.record()
+        torch.cuda.synchronize()
+        tms = k0.elapsed_time(k1)
+        ttps = B * tn / (tms * 1e-3)
+        topk_leg = {"workload": "same pool, temp 0.9, precision 26, topk 300", "tokens_per_sec": ttps,
+                    "bits_per_token": (int(tk.cursor.sum().item()) - c0) / (B * tn),
+                    "roofline_frac": ttps * ALGO_BYTES_PER_TOKEN / 1e9 / peaks()[0], "steps": tn,
+                    "rows_handed_to_exact_kernel": int(((tk.status & 4) != 0).sum().item())}
+        del tk
+
     # final gather of the cover tokens (the only collective; outside the hot path)
     gather_ms = None
     if world > 1:
@@ -350,6 +374,7 @@ def run_gpu_arm(args):
             "gpu_launches": 2 * K,   # per step: ac_fast_kernel + ac_step_kernel draining the hand-over queue
             "gather_ms": gather_ms,
             "codecs": codecs,
+            "topk300": topk_leg,
             "clocks": clocks,
         }
         print(json.dumps(line))
