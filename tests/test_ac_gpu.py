@@ -247,3 +247,66 @@ def test_device_statistics_match_oracle():
                 assert int(st.tokens[r, t]) == tr.token
                 np.testing.assert_allclose(got[r], stats, rtol=1e-9, atol=1e-12)
                 lo[r], hi[r], cur[r] = tr.lo, tr.hi, ncur
+
+
+@pytest.mark.parametrize("V,precision,topk,temp,scale,quant", [
+    (50257, 26, 300, 0.9, 3.0, 0.0),      # config 2's coder settings
+    (50257, 26, 2, 1.0, 3.0, 0.0),        # smallest top-k
+    (50257, 16, 17, 0.7, 3.0, 0.0),       # low precision: overfill in the rank form
+    (50257, 12, 512, 1.3, 1.0, 0.0),      # flat rows, largest top-k of the path, heavy overfill
+    (42001, 26, 300, 1.0, 8.0, 0.0),      # peaked rows: often fewer than topk tokens above the cutoff
+    (50257, 26, 64, 1.0, 3.0, 0.25),      # quantised logits: many exact ties across the top-k boundary
+    (5000, 20, 100, 1.0, 2.0, 0.5),       # small vocabulary, dense ties (boundary bucket overflow -> hand-over)
+])
+def test_rank_form_fast_path_matches_exact_kernel(V, precision, topk, temp, scale, quant):
+    """The top-k-binding path of the throughput kernel against the exact kernel, encode and decode: same
+    tokens, intervals, cursors, recovered bits; plus the oracle on a few streams."""
+    B, T, steps = 48, 4, 20
+    g = torch.Generator(device="cuda").manual_seed(1000 + topk)
+    pool = [torch.randn(B, V, generator=g, device="cuda") * scale for _ in range(T)]
+    if quant:
+        pool = [(p / quant).round() * quant for p in pool]
+    fn = lambda t: pool[t % T]
+    msgs = [message_bits(1500 + r, 256).tolist() for r in range(B)]
+    enc = {}
+    for force in (False, True):
+        st = _streams(B, V, precision=precision, temp=temp, topk=topk, token_cap=steps + 2, trace=True, force_exact=force)
+        st.set_messages(msgs)
+        st.encode(fn, poll_every=64, max_steps=steps)
+        enc[force] = st
+    a, b = enc[False], enc[True]
+    for name in ("tokens", "lo", "hi", "cursor", "ntok"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert int((a.status & 3).sum().item()) == 0
+    toks = a.token_lists()
+    dec = {}
+    for force in (False, True):
+        st = _streams(B, V, precision=precision, temp=temp, topk=topk, token_cap=steps + 2, force_exact=force)
+        st.set_tokens(toks)
+        dec[force] = st.decode(fn)
+    assert dec[False] == dec[True]
+    cur = a.cursor.cpu().numpy()
+    for r in range(B):
+        n = int(min(cur[r], len(msgs[r])))
+        assert dec[False][r][:n] == msgs[r][:n], r
+    for r in (0, B - 1):
+        rows = lambda t, r=r: pool[t % T][r].cpu().numpy()
+        res = O.encode_stream(rows, msgs[r], temp=temp, precision=precision, topk=topk, max_steps=steps)
+        assert toks[r][: len(res.tokens)] == res.tokens[: len(toks[r])], r
+
+
+def test_rank_form_decode_of_foreign_token():
+    """A cover token outside the top-k: flagged, coded as rank 0 (arithmetic.py:342), same as the exact kernel."""
+    V, B = 50257, 8
+    g = torch.Generator(device="cuda").manual_seed(77)
+    logits = torch.randn(B, V, generator=g, device="cuda") * 3.0
+    worst = logits.argmin(dim=1).cpu().tolist()
+    outs = []
+    for force in (False, True):
+        st = _streams(B, V, precision=26, temp=0.9, topk=300, token_cap=4, force_exact=force)
+        st.set_tokens([[w, w] for w in worst])
+        st.decode_step(logits)
+        outs.append((st.lo.clone(), st.hi.clone(), st.out_len.clone(), st.out_bits.clone(), (st.status & 1).clone()))
+    for x, y in zip(*outs):
+        assert torch.equal(x, y)
+    assert bool((outs[0][4] == 1).all().item())
