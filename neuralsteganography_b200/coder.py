@@ -123,8 +123,14 @@ class ArithmeticStreams:
         self.set_packed_messages(torch.from_numpy(words.view(np.int32)), torch.from_numpy(lens))
 
     def set_packed_messages(self, words_i32: torch.Tensor, lens_i32: torch.Tensor) -> None:
-        self.msg = words_i32.to(self.device, non_blocking=True).contiguous()
-        self.msg_len = lens_i32.to(self.device, non_blocking=True).contiguous()
+        # buffers are reused when the new messages fit, so that a captured CUDA graph stays valid across calls
+        if self.msg is not None and self.msg.shape[0] == words_i32.shape[0] and self.msg.shape[1] >= words_i32.shape[1]:
+            self.msg.zero_()
+            self.msg[:, : words_i32.shape[1]].copy_(words_i32, non_blocking=True)
+            self.msg_len.copy_(lens_i32, non_blocking=True)
+        else:
+            self.msg = words_i32.to(self.device, non_blocking=True).contiguous()
+            self.msg_len = lens_i32.to(self.device, non_blocking=True).contiguous()
         self.reset()
         self.tokens.fill_(-1)
         # empty messages never enter the loop (arithmetic.py:114)
@@ -144,15 +150,23 @@ class ArithmeticStreams:
 
     def set_token_tensor(self, tokens_i32: torch.Tensor, lens_i32: torch.Tensor,
                          out_bits_capacity: Optional[int] = None) -> None:
-        self.tokens = tokens_i32.to(self.device, non_blocking=True).contiguous()
+        # as in set_packed_messages: same shapes -> same buffers (CUDA graphs of the decode loop stay valid)
+        if self.tokens is not None and tuple(self.tokens.shape) == tuple(tokens_i32.shape) and self.ntok_total is not None:
+            self.tokens.copy_(tokens_i32, non_blocking=True)
+            self.ntok_total.copy_(lens_i32, non_blocking=True)
+        else:
+            self.tokens = tokens_i32.to(self.device, non_blocking=True).contiguous()
+            self.ntok_total = lens_i32.to(self.device, non_blocking=True).contiguous()
         self.token_cap = int(self.tokens.shape[1])
-        self.ntok_total = lens_i32.to(self.device, non_blocking=True).contiguous()
         self.reset()
         self.phase.copy_(torch.where(self.ntok_total > 0, 0, 2).to(torch.uint8))
         cap_bits = out_bits_capacity or (self.token_cap * self.precision + self.precision)
         words = (cap_bits + 31) // 32 + 2
-        self.out_bits = torch.zeros((self.B, words), dtype=torch.int32, device=self.device)
-        self.out_len = torch.zeros(self.B, dtype=torch.int32, device=self.device)
+        if self.out_bits is not None and tuple(self.out_bits.shape) == (self.B, words):
+            self.out_bits.zero_(); self.out_len.zero_()
+        else:
+            self.out_bits = torch.zeros((self.B, words), dtype=torch.int32, device=self.device)
+            self.out_len = torch.zeros(self.B, dtype=torch.int32, device=self.device)
 
     # ------------------------------------------------------------------ steps
     def _fill_common(self, logits: torch.Tensor) -> N.AcParams:

@@ -36,9 +36,10 @@ class StegoGenerator:
         self.collect_stats = bool(collect_stats)        # a6: NLL / KL / entropy sums (exact kernel, eager loop)
         self.stats_sum = torch.zeros(self.B, 3, dtype=torch.float64, device=self.device)
         self.stats_steps = 0
+        self._coders = {}
 
     # one loop iteration: coder on the current logits, then the trunk on the token just fixed
-    def _iter(self, coder: ArithmeticStreams, decode: bool) -> None:
+    def _iter(self, coder: ArithmeticStreams, decode: bool, kv_len: Optional[int] = None) -> None:
         if decode:
             coder.decode_step(self.logits)
         else:
@@ -51,21 +52,41 @@ class StegoGenerator:
                 self.stats_steps += int(coding.sum().item() > 0)
         last = (coder.ntok.long() - 1).clamp(min=0)
         prev = coder.tokens[self._rows, last].long().clamp(min=0)      # finished streams feed a stale token
-        self.logits.copy_(self.trunk.step(prev))
+        self.logits.copy_(self.trunk.step(prev, kv_len))
 
-    def _run(self, coder: ArithmeticStreams, decode: bool, max_steps: int, poll_every: int) -> None:
-        graph = None
+    def _coder(self, decode: bool, token_cap: int, kw: dict) -> ArithmeticStreams:
+        """Coder state (and with it the captured graphs) is kept across calls of the same shape."""
+        key = (decode, int(token_cap))
+        ent = self._coders.get(key)
+        if ent is None:
+            ent = {"coder": ArithmeticStreams(self.B, self.V, device=self.device, token_cap=token_cap, **kw), "graphs": {},
+                   "sig": None}
+            self._coders = {k: v for k, v in self._coders.items() if k[0] != decode}   # one shape per direction
+            self._coders[key] = ent
+        return ent
+
+    @staticmethod
+    def _signature(c: ArithmeticStreams):
+        return tuple(0 if t is None else t.data_ptr() for t in (c.msg, c.msg_len, c.tokens, c.ntok_total, c.out_bits, c.out_len))
+
+    def _run(self, ent: dict, decode: bool, max_steps: int, poll_every: int, ctx_len: int) -> None:
+        coder = ent["coder"]
+        sig = self._signature(coder)
+        if ent["sig"] != sig:                               # buffers moved: graphs captured on the old ones are stale
+            ent["graphs"], ent["sig"] = {}, sig
         t = 0
         while t < max_steps:
-            if self.use_graph and graph is None and t >= 2:
+            kv = self.trunk.kv_bucket(ctx_len + t + 1)      # host arithmetic only: the length is ctx_len + t
+            graph = ent["graphs"].get(kv) if self.use_graph and not self.collect_stats else None
+            if self.use_graph and not self.collect_stats and graph is None and (t >= 2 or ent["graphs"]):
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
-                    self._iter(coder, decode)
-                # capture does not execute: this step still has to run
+                    self._iter(coder, decode, kv)
+                ent["graphs"][kv] = graph                   # capture does not execute: this step still has to run
             if graph is not None:
                 graph.replay()
             else:
-                self._iter(coder, decode)
+                self._iter(coder, decode, kv)
             t += 1
             if t % poll_every == 0 and coder.all_done():
                 break
@@ -92,13 +113,14 @@ class StegoGenerator:
                max_tokens: Optional[int] = None) -> List[List[int]]:
         """Cover tokens for one message (list of 0/1) per stream."""
         room = self._room(contexts, max_tokens)
-        coder = ArithmeticStreams(self.B, self.V, device=self.device, token_cap=max(1, room), **self.kw)
+        ent = self._coder(False, max(1, room), self.kw)
+        coder = ent["coder"]
         coder.set_messages(messages)
         if self.collect_stats:
             coder.stats = torch.zeros(self.B, 3, dtype=torch.float64, device=self.device)
             self.stats_sum.zero_(); self.stats_steps = 0
         self._prefill(contexts)
-        self._run(coder, False, room, poll_every)
+        self._run(ent, False, room, poll_every, min(int(contexts.shape[-1]), 1022))
         self.coder = coder
         return coder.token_lists()
 
@@ -106,9 +128,10 @@ class StegoGenerator:
         """Recovered bits (message + trailing bits, as the reference returns them) per stream."""
         n = max((len(t) for t in token_lists), default=0)
         kw = dict(self.kw); kw["finish_sent"] = False
-        coder = ArithmeticStreams(self.B, self.V, device=self.device, token_cap=max(1, n), **kw)
+        ent = self._coder(True, max(1, n), kw)
+        coder = ent["coder"]
         coder.set_tokens(token_lists)
         self._prefill(contexts)
-        self._run(coder, True, n, poll_every)
+        self._run(ent, True, n, poll_every, min(int(contexts.shape[-1]), 1022))
         self.coder = coder
         return coder.bit_lists()

@@ -90,17 +90,31 @@ class StaticGPT2:
 
     # ------------------------------------------------------------------ one token (fixed shapes, graph-capturable)
     @torch.no_grad()
-    def step(self, tokens: torch.Tensor) -> torch.Tensor:
-        """Append ``tokens`` [B] (int64) at position ``length``; returns fp32 logits [B, V].  No host sync."""
+    def kv_bucket(self, needed: int) -> int:
+        """Smallest power-of-two prefix of the KV buffer (>= 64 slots) that holds ``needed`` entries; the whole
+        buffer once the ring is in use.  A decoding step only reads that prefix, so a graph per bucket keeps the
+        attention traffic proportional to the live length instead of the buffer size."""
+        if self.ring and needed > self.ring:
+            return self.T
+        b = 64
+        while b < needed:
+            b *= 2
+        return min(b, self.T)
+
+    def step(self, tokens: torch.Tensor, kv_len: Optional[int] = None) -> torch.Tensor:
+        """Append ``tokens`` [B] (int64) at position ``length``; returns fp32 logits [B, V].  No host sync.
+        ``kv_len`` (host int, >= length + 1): only that prefix of the KV buffers is attended to."""
         B = self.B
+        Tk = self.T if kv_len is None else int(kv_len)
+        ar = self._arange_t[:Tk]
         if self.ring:
             pos = self.length.clamp(max=self.window).remainder(self.n_positions).view(1)   # cache length, then :44-48
             slot = self.length.remainder(self.ring).view(1)                          # overwrites the entry limit_past dropped
-            live = ((self._arange_t <= self.length) & (self._arange_t < self.ring))[None, None, None, :]
+            live = ((ar <= self.length) & (ar < self.ring))[None, None, None, :]
         else:
             pos = self.length.remainder(self.n_positions).view(1)                    # arithmetic.py:44-48
             slot = self.length.clamp(max=self.T - 1).view(1)                         # device index: no host sync
-            live = (self._arange_t <= self.length)[None, None, None, :]              # keys 0..length
+            live = (ar <= self.length)[None, None, None, :]                          # keys 0..length
         x = self.wte.index_select(0, tokens) + self.wpe.index_select(0, pos)         # tensor indices: no host sync
         for i, w in enumerate(self.layers):
             h = F.layer_norm(x, (self.n_embd,), w["ln1w"], w["ln1b"], self.eps)
@@ -111,9 +125,10 @@ class StaticGPT2:
             v = v.view(B, self.n_head, 1, self.hd)
             self.k[i].index_copy_(2, slot, k)                                        # cache row `length`
             self.v[i].index_copy_(2, slot, v)
-            att = (q @ self.k[i].transpose(-1, -2)) / math.sqrt(self.hd)             # [B, H, 1, T]
+            kk, vv = self.k[i][:, :, :Tk], self.v[i][:, :, :Tk]                      # views: the live prefix
+            att = (q @ kk.transpose(-1, -2)) / math.sqrt(self.hd)                    # [B, H, 1, Tk]
             att = att.masked_fill(~live, torch.finfo(att.dtype).min).softmax(-1)
-            a = (att @ self.v[i]).reshape(B, self.n_embd)
+            a = (att @ vv).reshape(B, self.n_embd)
             x = x + (a @ w["pw"] + w["pb"])
             h = F.layer_norm(x, (self.n_embd,), w["ln2w"], w["ln2b"], self.eps)
             x = x + (F.gelu(h @ w["fcw"] + w["fcb"], approximate="tanh") @ w["ow"] + w["ob"])

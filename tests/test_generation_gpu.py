@@ -22,8 +22,8 @@ def _replay_logits(model, ctx, tokens, max_len=128):
     from neuralsteganography_b200.trunk import StaticGPT2
     tr = StaticGPT2(model, 1, max_len=max_len)
     rows = [tr.prefill(ctx[None].cuda())[0].cpu().numpy()]
-    for t in tokens[:-1]:
-        rows.append(tr.step(torch.tensor([t], device="cuda"))[0].cpu().numpy())
+    for s, t in enumerate(tokens[:-1]):                      # same KV prefix per step as the generation loop
+        rows.append(tr.step(torch.tensor([t], device="cuda"), tr.kv_bucket(len(ctx) + s + 1))[0].cpu().numpy())
     return rows
 
 
@@ -119,7 +119,7 @@ def test_generation_slides_the_1022_token_window():
         assert bits[r][: len(msgs[r])] == msgs[r], r
     tr = StaticGPT2(model, 1, max_len=1024)
     rows = [tr.prefill(ctx[None].cuda())[0].cpu().numpy()]
-    for t in toks[0][:-1]:
-        rows.append(tr.step(torch.tensor([t], device="cuda"))[0].cpu().numpy())
+    for s, t in enumerate(toks[0][:-1]):
+        rows.append(tr.step(torch.tensor([t], device="cuda"), tr.kv_bucket(len(ctx) + s + 1))[0].cpu().numpy())
     res = O.encode_stream(lambda t: rows[t], msgs[0], temp=1.0, precision=16, topk=2048, max_steps=len(rows))
     assert res.tokens == toks[0]

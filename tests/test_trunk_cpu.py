@@ -79,3 +79,20 @@ def test_short_buffer_matches_until_it_fills():
     for s in range(steps):
         tok = torch.randint(0, 96, (B,), generator=g)
         assert torch.allclose(trunk.step(tok), naive.call(tok[:, None]), atol=2e-5), s
+
+
+def test_kv_bucket_prefix_gives_the_same_logits():
+    """Attending to the live power-of-two prefix of the KV buffer (what the captured graphs do) changes nothing."""
+    model = _tiny()
+    B, L = 2, 40
+    a = StaticGPT2(model, B, max_len=256, device="cpu")
+    b = StaticGPT2(model, B, max_len=256, device="cpu")
+    assert [a.kv_bucket(n) for n in (1, 64, 65, 128, 129, 300)] == [64, 64, 128, 128, 256, 256]
+    g = torch.Generator().manual_seed(5)
+    ctx = torch.randint(0, 96, (B, L), generator=g)
+    assert torch.allclose(a.prefill(ctx), b.prefill(ctx))
+    for s in range(40):                                           # crosses the 64-slot bucket at step 24
+        tok = torch.randint(0, 96, (B,), generator=g)
+        assert torch.allclose(a.step(tok), b.step(tok, b.kv_bucket(L + s + 1)), atol=1e-6), s
+    ring = StaticGPT2(model, B, max_len=1024, device="cpu")
+    assert ring.kv_bucket(1023) == 1024 and ring.kv_bucket(1024) == 1024 and ring.kv_bucket(5000) == 1024
