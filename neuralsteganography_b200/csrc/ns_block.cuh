@@ -58,11 +58,14 @@ __device__ __forceinline__ u64 block_reduce_u(u64 v, Op op, u64* scratch) {
   __syncthreads();
   if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
   __syncthreads();
-  u64 r = scratch[0];
-#pragma unroll 1
-  for (int w = 1; w < NWARPS; ++w) r = op(r, scratch[w]);
+  // NWARPS == 32 partials: one per lane, a second butterfly (the operators are exact and commutative, so the
+  // order does not matter and every thread ends with the same value)
+  u64 r = scratch[threadIdx.x & 31];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) r = op(r, __shfl_xor_sync(0xffffffffu, r, o));
   return r;
 }
+static_assert(NWARPS == 32, "block_reduce_u combines one partial per lane");
 
 __device__ __forceinline__ double block_sum_d(double v, u64* scratch) {
 #pragma unroll
@@ -131,22 +134,36 @@ __device__ void sel_locate(const HistT* hist, u64 tau, Scalars* sc) {
   __syncthreads();
 }
 
-// Exact resolution among the collected entries of the target bucket.
+// Exact resolution among the collected entries of the target bucket.  The n x n comparisons are spread over the
+// whole CTA: a group of `ways` adjacent lanes shares one entry, each lane scans every ways-th other entry, and
+// the partial weights meet by shuffles (integer sums: exact in any order).
 __device__ void sel_resolve(const ListEntry* list, int n, u64 tau, u64 prefix, Scalars* sc) {
   if (threadIdx.x == 0) sc->res_found = 0;
   __syncthreads();
-  for (int c = threadIdx.x; c < n; c += NT) {
-    const u64 pc = list[c].pack, wc = list[c].w;
-    u64 before = prefix;
-    for (int o = 0; o < n; ++o) {
-      const u64 po = list[o].pack;
-      if (po > pc) before += list[o].w;
+  int ways = 1;
+  while (ways < 8 && n * ways * 2 <= NT) ways *= 2;          // 1, 2, 4 or 8 lanes per entry (uniform across the CTA)
+  const int sub = threadIdx.x & (ways - 1);
+  for (int base = 0; base < n; base += NT / ways) {          // one trip unless n > NT (never: n <= LIST_CAP)
+    const int c = base + threadIdx.x / ways;
+    const bool live = c < n;
+    const u64 pc = live ? list[c].pack : 0ull;
+    u64 before = 0;
+    if (live) {
+      for (int o = sub; o < n; o += ways) {
+        const u64 po = list[o].pack;
+        if (po > pc) before += list[o].w;
+      }
     }
-    if (wc != 0 && before <= tau && tau < before + wc) {
-      sc->res_idx = id_of_pack(pc);
-      sc->res_before = before;
-      sc->res_w = wc;
-      sc->res_found = 1;
+    for (int o = 1; o < ways; o <<= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    if (live && sub == 0) {
+      const u64 wc = list[c].w;
+      before += prefix;
+      if (wc != 0 && before <= tau && tau < before + wc) {
+        sc->res_idx = id_of_pack(pc);
+        sc->res_before = before;
+        sc->res_w = wc;
+        sc->res_found = 1;
+      }
     }
   }
   __syncthreads();

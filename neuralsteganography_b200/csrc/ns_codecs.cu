@@ -155,10 +155,10 @@ __device__ float* stage_row_bulk(const ns_codec_params& P, int row, CodecShared&
   __syncthreads();                                           // fixes of other threads visible; red free
   if ((tid & 31) == 0) { sm.sc->red[tid >> 5] = a; reinterpret_cast<u64*>(sm.list)[tid >> 5] = b; }
   __syncthreads();
-  u64 ra = sm.sc->red[0], rb = reinterpret_cast<u64*>(sm.list)[0];
-#pragma unroll 1
-  for (int w = 1; w < NWARPS; ++w) {
-    const u64 x = sm.sc->red[w], y = reinterpret_cast<u64*>(sm.list)[w];
+  u64 ra = sm.sc->red[tid & 31], rb = reinterpret_cast<u64*>(sm.list)[tid & 31];   // one partial per lane
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const u64 x = __shfl_xor_sync(0xffffffffu, ra, o), y = __shfl_xor_sync(0xffffffffu, rb, o);
     ra = x > ra ? x : ra;
     rb = y < rb ? y : rb;
   }
@@ -358,18 +358,28 @@ __global__ void __launch_bounds__(NT, 1) rank_kernel(ns_codec_params P) {
     if (tid == 0) sm.sc->list_count = 0;
     __syncthreads();
   }
-  uint32_t cnt = 0, before = 0;
+  // branch-free: certain tokens and "within a hair of the bound" tokens are counted apart; the fp64 test runs
+  // only if the second count is not zero (practically never)
+  uint32_t cnt = 0, maybe = 0, before = 0;
   for (int i = tid; i < V; i += NT) {
     const float k = keys[i];
-    cnt += positive(k) ? 1u : 0u;
+    cnt += k > k_yes ? 1u : 0u;
+    maybe += (k >= k_no && !(k > k_yes)) ? 1u : 0u;
     if (DECODE) before += pack_of(k, i) > tp ? 1u : 0u;
     else atomicAdd(&sm.hist[bin_of(k, m, scale, NB)], 1u);
   }
-  const u64 both = block_reduce_u(((u64)before << 32) | (u64)cnt, OpAddU(), sm.sc->red);
-  const u64 total_pos = both & 0xffffffffull;
+  const u64 both = block_reduce_u(((u64)before << 40) | ((u64)maybe << 20) | (u64)cnt, OpAddU(), sm.sc->red);
+  u64 total_pos = both & 0xfffffull;
+  if ((both >> 20) & 0xfffffull) {
+    u64 c2 = 0;
+    for (int i = tid; i < V; i += NT) {
+      const float k = keys[i];
+      if (k >= k_no && !(k > k_yes) && positive(k)) c2 += 1;
+    }
+    total_pos += block_reduce_u(c2, OpAddU(), sm.sc->red);
+  }
   if (total_pos < n_pos) n_pos = total_pos;
-  int capacity = 0;
-  while ((2ull << capacity) <= n_pos) ++capacity;                       // floor(log2(n_pos)), :379
+  const int capacity = n_pos ? 63 - __clzll((long long)n_pos) : 0;      // floor(log2(n_pos)), :379
   if (capacity <= 0) {                                                  // ArithmeticRangeError :149
     if (tid == 0 && P.status) atomicOr(&P.status[row], NS_ST_OUT_OF_RANGE);
     if (tid == 0 && P.phase) P.phase[row] = NS_PHASE_DONE;
@@ -384,7 +394,7 @@ __global__ void __launch_bounds__(NT, 1) rank_kernel(ns_codec_params P) {
     if (consumed > capacity) consumed = capacity;                       // :155
     if (tid == 0) emit_token(P, row, slot, token, consumed);
   } else {
-    const u64 rank = both >> 32;                                        // ranked_tokens.index(token), :211
+    const u64 rank = both >> 40;                                        // ranked_tokens.index(token), :211
     if (tid == 0) {
       if (rank >= (1ull << capacity) && P.status) atomicOr(&P.status[row], NS_ST_OUT_OF_RANGE);   // :212-213
       const int total = P.total_bits ? P.total_bits[row] : 0x7fffffff;
