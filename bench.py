@@ -183,7 +183,8 @@ def run_gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    B = args.streams
+    # weak scaling (the contract's default): --streams per GPU; --strong: --streams in total, split over the ranks
+    B = args.streams if not args.strong else max(1, args.streams // world)
     K, W = args.steps, max(3, args.warmup)
     # synthetic inputs: pool of logits, random messages
     pool = []
@@ -354,7 +355,7 @@ def run_gpu_arm(args):
         achieved = ALGO_BYTES_PER_TOKEN * B / kernel_s / 1e9
         line = {
             "metric": METRIC, "value": tps, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "streams_per_gpu": B, "vocab": V, "precision": PRECISION, "temp": TEMP,
                        "topk": V, "l2": "inputs larger than L2: 4-entry logits pool, 823 MB per step",
@@ -394,6 +395,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--codec-steps", type=int, default=8)
     ap.add_argument("--no-codecs", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: --streams is the total over all ranks")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
