@@ -271,83 +271,88 @@ __device__ __noinline__ int fast_rank_row(const ns_ac_params& P, int32_t* slow_w
   auto lap = [&](int k) { if (P.prof && tid == 0) { const long long t = clock64(); atomicAdd((unsigned long long*)&P.prof[k], (unsigned long long)(t - tq)); tq = t; } };
   const float span = M - kappa_r;
   if (!(span > 0.0f)) return 0;
-  const float rscale = (float)F_NB / span;
-  // monotone bucket of a key without a conversion instruction: (M - v) * rscale, clamped, rounded by the
-  // 2^23 trick; the low mantissa bits are the bucket
-  const float b_off = M * rscale + 8388608.0f, b_max = 8388608.0f + (float)(F_NB - 1);
-  auto bucket = [&](float v) -> int {
-    return __float_as_int(fmaxf(fminf(fmaf(-v, rscale, b_off), b_max), 8388608.0f)) & (F_NB - 1);
+  // monotone bucket of a key without a conversion instruction: (M - v) * scale, clamped, rounded by the 2^23
+  // trick; the low mantissa bits are the bucket
+  const float b_max = 8388608.0f + (float)(F_NB - 1);
+  auto bucket_of = [&](float v, float scale, float off) -> int {
+    return __float_as_int(fmaxf(fminf(fmaf(-v, scale, off), b_max), 8388608.0f)) & (F_NB - 1);
   };
-  // ---- pass A: count histogram of the keys certainly above the cutoff (padding and masks are -inf).
-  // Branch-free: keys below the cutoff add 0 to a bucket of the lane's own
-  auto count = [&](float v) {
-    const uint32_t inc = v >= kappa_r ? 1u : 0u;
-    atomicAdd(hist + (inc ? bucket(v) : (tid & (F_NB - 1))), inc);
+  // block scan of the histogram: F_BPT buckets per thread; returns this thread's exclusive prefix and the total
+  uint32_t hloc[F_BPT];
+  auto scan_hist = [&](uint32_t* excl_out, uint32_t* total_out) {
+    uint32_t tsum = 0;
+#pragma unroll
+    for (int b = 0; b < F_BPT; ++b) { hloc[b] = hist[tid * F_BPT + b]; tsum += hloc[b]; }
+    uint32_t inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    __syncthreads();                                       // the previous user of sc->red is done
+    if (lane == 31) sc->red[warp] = inc;
+    if (tid == 0) { sc->sel_bin = -1; sc->sel_prefix = 0; }
+    __syncthreads();
+    uint32_t woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < FW; ++w) { const uint32_t x = (uint32_t)sc->red[w]; if (w < warp) woff += x; total += x; }
+    *excl_out = woff + inc - tsum;
+    *total_out = total;
   };
-  for (int c = tid; c < W4; c += 2 * FT) {
-    const float4 v = w4[c];
-    const float4 w = (c + FT < W4) ? w4[c + FT] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-    count(v.x); count(v.y); count(v.z); count(v.w);
-    count(w.x); count(w.y); count(w.z); count(w.w);
+  // bucket holding position `pos` of the scanned histogram -> sc->sel_bin / sel_prefix (after a barrier)
+  auto locate_pos = [&](uint32_t excl, uint32_t pos) {
+#pragma unroll
+    for (int b = 0; b < F_BPT; ++b) {
+      if (hloc[b] != 0 && excl <= pos && pos < excl + hloc[b]) { sc->sel_bin = tid * F_BPT + b; sc->sel_prefix = excl; }
+      excl += hloc[b];
+    }
+    __syncthreads();
+  };
+  auto clear_hist = [&]() {
+#pragma unroll
+    for (int b = 0; b < F_BPT; ++b) hist[tid * F_BPT + b] = 0;
+  };
+
+  // ---- level 1: count histogram of a 1/8 sample (whole warp iterations, spread over the ids) of the keys
+  // certainly above the cutoff -> a key k_c that bounds the top-k from below with ~1.5 K candidates above it.
+  // Branch-free inside a sampled iteration: keys below the cutoff add 0 to a bucket of the lane's own.
+  const float rscale = (float)F_NB / span, b_off = M * rscale + 8388608.0f;
+  {
+    int it = 0;
+    for (int cw = tid - lane; cw < W4; cw += 2 * FT, ++it) {
+      if (((it + warp) & 7) != 0) continue;                // warp-uniform
+      const int c = cw + lane;
+      const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      const float4 v = (c < W4) ? w4[c] : ninf;
+      const float4 w = (c + FT < W4) ? w4[c + FT] : ninf;
+      const float xs[8] = {v.x, v.y, v.z, v.w, w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const uint32_t inc = xs[e] >= kappa_r ? 1u : 0u;
+        atomicAdd(hist + (inc ? bucket_of(xs[e], rscale, b_off) : (tid & (F_NB - 1))), inc);
+      }
+    }
   }
   __syncthreads();
   lap(11);
-  uint32_t hloc[F_BPT], tsum = 0;
-#pragma unroll
-  for (int b = 0; b < F_BPT; ++b) { hloc[b] = hist[tid * F_BPT + b]; tsum += hloc[b]; }
-  uint32_t inc = tsum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-  if (lane == 31) sc->red[warp] = inc;
-  if (tid == 0) { sc->sel_bin = -1; sc->sel_prefix = 0; }
-  __syncthreads();
-  uint32_t woff = 0, total = 0;
-#pragma unroll
-  for (int w = 0; w < FW; ++w) { const uint32_t x = (uint32_t)sc->red[w]; if (w < warp) woff += x; total += x; }
-  if (total <= (uint32_t)K) {                              // not certainly rank form: clean up, threshold form decides
-    __syncthreads();
-#pragma unroll
-    for (int b = 0; b < F_BPT; ++b) hist[tid * F_BPT + b] = 0;
-    __syncthreads();
-    return 0;
-  }
-  // ---- bucket of position K-1; every bucket becomes (count | exclusive prefix << 16) for the gather
+  float k_c = kappa_r;
   {
-    uint32_t excl = woff + inc - tsum;
-#pragma unroll
-    for (int b = 0; b < F_BPT; ++b) {
-      if (hloc[b] != 0 && excl <= (uint32_t)(K - 1) && (uint32_t)(K - 1) < excl + hloc[b]) { sc->sel_bin = tid * F_BPT + b; sc->sel_prefix = excl; }
-      hist[tid * F_BPT + b] = hloc[b] | ((excl < 0xffffu ? excl : 0xffffu) << 16);
-      excl += hloc[b];
+    uint32_t excl, total_s;
+    scan_hist(&excl, &total_s);
+    const uint32_t r_s = (uint32_t)((3 * K) / 16 + 12);    // 1.5 K / 8 plus a margin of > 5 sigma of the sample count
+    if (total_s > r_s) {
+      locate_pos(excl, r_s - 1u);
+      // lower key edge of that sample bucket (round-to-nearest buckets: b covers [b - 0.5, b + 0.5)), one more
+      // bucket of slack for the rounding of the offset
+      k_c = fmaxf(kappa_r, M - ((float)sc->sel_bin + 1.5f) / rscale);
     }
+    __syncthreads();
+    clear_hist();
   }
-  __syncthreads();
-  const int tb = sc->sel_bin;
-  const int prefix = (int)sc->sel_prefix;                  // tokens in the buckets before tb: all kept
-  lap(12);
-  // ---- pass B: gather.  Buckets before tb land grouped by bucket at their prefix; tb goes to the boundary list
-  auto gather = [&](float v, int id) {
-    if (v >= kappa_r) {
-      const int b = bucket(v);
-      if (b < tb) {
-        const uint32_t old = atomicSub(&hist[b], 1u);        // low 16 bits: slots still free in the bucket
-        const uint32_t cnt_left = old & 0xffffu, ex = old >> 16;
-        CandEntry e; e.ebits = ex; e.id = id; e.w = 0u; e.key = v + 0.0f;
-        top[ex + cnt_left - 1u] = e;
-      } else if (b == tb) {
-        const int s2 = atomicAdd(&sc->u_n, 1);
-        if (s2 < F_RB_CAP) { bnd[s2].id = id; bnd[s2].kept = __float_as_int(v + 0.0f); }
-      }
-    }
-  };
-  // keys that can fall into buckets <= tb (a hair loose; `gather` decides exactly) are rare per element but
-  // present in almost every warp iteration, so the pass only lists their ids (a few predicated instructions per
-  // element); the listed tokens are then gathered one per thread.  The list borrows the exp table's words.
-  const float k_hit = M - ((float)tb + 1.5f) / rscale;
-  int* cand = reinterpret_cast<int*>(const_cast<double*>(tab));
-  constexpr int CAND_CAP = NS_EXP_N * 2;
-  // first a branch-free sweep that only marks, per thread, the iterations whose eight keys hold a hit (one bit
-  // each); then every thread revisits its few marked iterations and lists the ids
+  // ---- list the ids of the keys >= k_c.  Hits are rare per element but present in almost every warp iteration:
+  // a branch-free sweep marks, per thread, the iterations whose eight keys hold a hit (one bit each); then every
+  // thread revisits its few marked iterations.  The list lives where the gathered entries go later (each thread
+  // has its listed tokens in registers by then).
+  int* cand = reinterpret_cast<int*>(top);
+  constexpr int CAND_CAP = 4 * FT;                         // <= 2 * F_C_CAP * 16 / 4 ints
+  static_assert(CAND_CAP * 4 <= 2 * F_C_CAP * 16, "candidate list must fit the gathered-entry area");
   uint32_t marks = 0;
   {
     int it = 0;
@@ -355,33 +360,81 @@ __device__ __noinline__ int fast_rank_row(const ns_ac_params& P, int32_t* slow_w
       const float4 v = w4[c];
       const float4 w = (c + FT < W4) ? w4[c + FT] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
       const float mx = fmaxf(fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)), fmaxf(fmaxf(w.x, w.y), fmaxf(w.z, w.w)));
-      marks |= (mx >= k_hit ? 1u : 0u) << it;
+      marks |= (mx >= k_c ? 1u : 0u) << it;
     }
   }
-  auto note = [&](float v, int id) {
-    if (v >= k_hit) { const int s2 = atomicAdd(&sc->c_n, 1); if (s2 < CAND_CAP) cand[s2] = id; }
-  };
   while (marks) {
     const int it = __ffs(marks) - 1;
     marks &= marks - 1u;
     const int c = tid + it * 2 * FT;
     const float4 v = w4[c];
-    const int id = 4 * c - mis;
-    note(v.x, id); note(v.y, id + 1); note(v.z, id + 2); note(v.w, id + 3);
-    if (c + FT < W4) {
-      const float4 w = w4[c + FT];
-      const int id2 = 4 * (c + FT) - mis;
-      note(w.x, id2); note(w.y, id2 + 1); note(w.z, id2 + 2); note(w.w, id2 + 3);
+    const float4 w = (c + FT < W4) ? w4[c + FT] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    const float xs[8] = {v.x, v.y, v.z, v.w, w.x, w.y, w.z, w.w};
+    uint32_t hits = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) hits |= (xs[e] >= k_c ? 1u : 0u) << e;
+    while (hits) {                                         // one or two per revisit
+      const int e = __ffs(hits) - 1;
+      hits &= hits - 1u;
+      const int s2 = atomicAdd(&sc->c_n, 1);
+      if (s2 < CAND_CAP) cand[s2] = 4 * (e < 4 ? c : c + FT) - mis + (e & 3);
     }
   }
   __syncthreads();
   const int ncand = sc->c_n;
-  if (ncand <= CAND_CAP) {
-    for (int j = tid; j < ncand; j += FT) { const int id = cand[j]; gather(words[id + mis], id); }
+  if (ncand > CAND_CAP || ncand <= K) {
+    // too many ties / a flat row for the list, or (k_c == kappa_r) not more than K keys above the cutoff: not a
+    // row for this path.  The histogram is clean.
+    if (ncand > CAND_CAP) { if (tid == 0) hand_over(P, slow_ws, row, F_WHY_BUCKET); return 1; }
+    return 0;
+  }
+  lap(12);
+  // ---- level 2: count histogram of the listed keys over [k_c, M], bucket of position K-1, gather: buckets before
+  // it land grouped by bucket at their prefix (count | exclusive prefix << 16 per bucket), the boundary bucket
+  // goes to its own list
+  const float span2 = M - k_c;
+  const float rscale2 = span2 > 0.0f ? (float)F_NB / span2 : 0.0f, b_off2 = M * rscale2 + 8388608.0f;
+  float ck[4]; int cid[4], cb[4];                          // this thread's (up to four) listed tokens
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int j = tid + u * FT;
+    cid[u] = -1; ck[u] = 0.0f; cb[u] = 0;
+    if (j < ncand) {
+      cid[u] = cand[j];
+      ck[u] = words[cid[u] + mis];
+      cb[u] = bucket_of(ck[u], rscale2, b_off2);
+      atomicAdd(&hist[cb[u]], 1u);
+    }
   }
   __syncthreads();
-  for (int i = tid; i < NS_EXP_N; i += FT) const_cast<double*>(tab)[i] = c_exp_tab[i];   // the table is back
-  if (ncand > CAND_CAP) { __syncthreads(); if (tid == 0) hand_over(P, slow_ws, row, F_WHY_BUCKET); return 1; }
+  {
+    uint32_t excl, total2;
+    scan_hist(&excl, &total2);
+    uint32_t e2 = excl;
+#pragma unroll
+    for (int b = 0; b < F_BPT; ++b) {
+      hist[tid * F_BPT + b] = hloc[b] | ((e2 < 0xffffu ? e2 : 0xffffu) << 16);
+      e2 += hloc[b];
+    }
+    locate_pos(excl, (uint32_t)(K - 1));
+  }
+  const int tb = sc->sel_bin;
+  const int prefix = (int)sc->sel_prefix;                  // tokens in the buckets before tb: all kept
+  // (every thread read its list entries before the scan's barriers: the list words may be overwritten now)
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    if (cid[u] >= 0) {
+      if (cb[u] < tb) {
+        const uint32_t old = atomicSub(&hist[cb[u]], 1u);    // low 16 bits: slots still free in the bucket
+        const uint32_t cnt_left = old & 0xffffu, ex = old >> 16;
+        CandEntry e; e.ebits = ex; e.id = cid[u]; e.w = 0u; e.key = ck[u] + 0.0f;
+        top[ex + cnt_left - 1u] = e;
+      } else if (cb[u] == tb) {
+        const int s2 = atomicAdd(&sc->u_n, 1);
+        if (s2 < F_RB_CAP) { bnd[s2].id = cid[u]; bnd[s2].kept = __float_as_int(ck[u] + 0.0f); }
+      }
+    }
+  }
   __syncthreads();
   lap(13);
   const int nbnd = sc->u_n;

@@ -10,7 +10,7 @@ pool = [torch.randn(B, V, generator=g, device="cuda") * 3.0 for _ in range(P)]
 rng = np.random.default_rng(0)
 words = rng.integers(0, 1 << 32, size=(B, 130), dtype=np.uint64).astype(np.uint32)
 names = ["prologue", "L wait+estimate", "reduce+consts", "P1 exp pass", "FIX", "P2 q pass", "fixups+scan", "overfill sel",
-         "target sel", "epilogue", "row-top barrier", "  rank: histogram pass", "  rank: scan+locate", "  rank: list+gather",
+         "target sel", "epilogue", "row-top barrier", "  rank: sample histogram", "  rank: scan + list candidates", "  rank: level-2 histogram + gather",
          "  rank: boundary+order+exp"]
 for mode in ("enc", "dec"):
     st = ArithmeticStreams(B, V, precision=26, temp=TEMP, topk=TOPK, token_cap=32)
