@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from neuralsteganography_b200.generation import StegoGenerator
 from neuralsteganography_b200.lm import random_init_model
-from oracle.inputs import message_bits
+import numpy as np
 
 B = int(os.environ.get("STREAMS", "256"))
 BITS = int(os.environ.get("BITS", "1024"))
@@ -13,7 +13,7 @@ dtype = {"fp32": torch.float32, "bf16": torch.bfloat16}[os.environ.get("TRUNK", 
 _tok, model = random_init_model("gpt2")
 model = model.cuda()
 ctx = torch.tensor([50256, 11, 22])
-msgs = [message_bits(10 + r, BITS).tolist() for r in range(B)]
+msgs = [np.random.default_rng(10 + r).integers(0, 2, BITS).tolist() for r in range(B)]
 for graph in (True, False):
     gen = StegoGenerator(model, B, max_len=512, precision=26, temp=0.9, topk=300, use_graph=graph, trunk_dtype=dtype)
     gen.encode(ctx, msgs, poll_every=32)            # warm-up (builds, captures)

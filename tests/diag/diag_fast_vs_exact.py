@@ -1,7 +1,7 @@
 """Lock-step comparison of the throughput kernel and the exact kernel; on the first difference print
 both traces and the oracle's answer for that row."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from neuralsteganography_b200.coder import ArithmeticStreams
 from oracle import ac_oracle as O

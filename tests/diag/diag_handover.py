@@ -1,6 +1,6 @@
 """Print why rows were handed to the exact kernel (status bits 8..15), for a few input families."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from neuralsteganography_b200.coder import ArithmeticStreams
 from oracle.inputs import message_bits
