@@ -600,7 +600,7 @@ __device__ __forceinline__ void c_mbar_arrive(u64* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(c_saddr(bar)) : "memory");
 }
 __global__ void __launch_bounds__(BT + 32, 1) bins_stream_kernel(ns_codec_params P, int lut_bytes) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ u64 red[BT / 32];
   __shared__ u64 full[BINS_RING], empty[BINS_RING];
   __shared__ BinsRow meta[BT];

@@ -384,7 +384,9 @@ __device__ __noinline__ int fast_rank_row(const ns_ac_params& P, int32_t* slow_w
   const int ncand = sc->c_n;
   if (ncand > CAND_CAP || ncand <= K) {
     // too many ties / a flat row for the list, or (k_c == kappa_r) not more than K keys above the cutoff: not a
-    // row for this path.  The histogram is clean.
+    // row for this path.  The histogram is clean; the list counter goes back to zero for the threshold form.
+    __syncthreads();
+    if (tid == 0) sc->c_n = 0;
     if (ncand > CAND_CAP) { if (tid == 0) hand_over(P, slow_ws, row, F_WHY_BUCKET); return 1; }
     return 0;
   }
@@ -957,6 +959,125 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     };
 
     pc.mark(4);                                            // FIX: sums, band, verification, constants
+    // ------------------------------------------------------------------ decode without a histogram
+    // The observed token is known, so the mass ranked before it is a conditional sum over the row: no
+    // shared-memory reductions, no bucket scan, no gather.  Tokens whose truncated e equals the token's go to a
+    // small list and are ordered exactly (original logit, then id).  Only if the widths overfill the range
+    // (arithmetic.py:153-155, about one row in a hundred) the general path below runs instead.
+    if (MODE == MODE_DEC) {
+      int tok = meta.tok;
+      if (tok < 0 || tok >= V) tok = top_id;
+      float e32t = word_ld1(tok + mis);
+      bool tok_in_band = false;
+      if (__float_as_uint(e32t) == 0u) {
+        for (int k = 0; k < nband; ++k)
+          if (band[k].id == tok && band[k].kept) { e32t = f_pack_e(band[k].e); tok_in_band = true; }
+      }
+      const uint32_t tbits = __float_as_uint(e32t);          // 0: the token is not in the kept set
+      uint32_t qs = 0, bs32 = 0;                             // per-thread sums fit: the whole row's widths are < 2^32
+      auto tie_push = [&](int id, uint32_t q) {
+        const int s2 = atomicAdd(&sc->c_n, 1);
+        if (s2 < F_C_CAP) { clist[s2].ebits = tbits; clist[s2].id = id; clist[s2].w = q; clist[s2].key = 0.0f; }
+      };
+      auto d2_slow = [&](const float4 v, const int b, const uint32_t* qv, const bool* kv) {
+        const float ev[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t bits = __float_as_uint(ev[j]);
+          if (!kv[j]) { const int s2 = atomicAdd(&sc->u_n, 1); if (s2 < F_U_CAP) ulist[s2] = b + j; }
+          else if (qv[j]) {
+            qs += qv[j];
+            if (bits > tbits) bs32 += qv[j];
+            else if (bits == tbits && b + j != tok) tie_push(b + j, qv[j]);
+          }
+        }
+      };
+      for (int c = tid; c < W4; c += 2 * FT) {
+        const float4 v = word_ld4(c);
+        const float4 w = (c + FT < W4) ? word_ld4(c + FT) : make_float4(0.f, 0.f, 0.f, 0.f);   // packed 0: no-op
+        const int b = 4 * c - mis;
+        uint32_t q[8];
+        bool k[8];
+        k[0] = quick_mass(v.x, &q[0]); k[1] = quick_mass(v.y, &q[1]); k[2] = quick_mass(v.z, &q[2]); k[3] = quick_mass(v.w, &q[3]);
+        k[4] = quick_mass(w.x, &q[4]); k[5] = quick_mass(w.y, &q[5]); k[6] = quick_mass(w.z, &q[6]); k[7] = quick_mass(w.w, &q[7]);
+        const uint32_t bt[8] = {__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w),
+                                __float_as_uint(w.x), __float_as_uint(w.y), __float_as_uint(w.z), __float_as_uint(w.w)};
+        bool tie = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tie |= (bt[j] == tbits);
+        if ((k[0] & k[1] & k[2] & k[3] & k[4] & k[5] & k[6] & k[7]) && !(tie && tbits != 0u)) {   // e32 == 0 yields q == 0
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { qs += q[j]; bs32 += bt[j] > tbits ? q[j] : 0u; }
+        } else {
+          d2_slow(v, b, q, k);
+          d2_slow(w, b + 4 * FT, q + 4, k + 4);
+        }
+      }
+      pc.mark(5);
+      __syncthreads();
+      const int nu = sc->u_n;
+      if (nu > F_U_CAP) { if (tid == 0) hand_over(P, slow_ws, row, F_WHY_ULIST); return; }
+      for (int u = tid; u < nu; u += FT) {                     // widths the truncated e could not decide
+        const int id = ulist[u];
+        const uint32_t m = exact_mass(id), bits = __float_as_uint(word_ld1(id + mis));
+        qs += m;
+        if (bits > tbits) bs32 += m;
+        else if (bits == tbits && id != tok && m) tie_push(id, m);
+      }
+      if (tid < nband && band[tid].kept) {                     // the exact-list band
+        const double e = band[tid].e;
+        const uint32_t m = (uint32_t)__double2ll_rn(e * C), bits = __float_as_uint(f_pack_e(e));
+        qs += m;
+        if (bits > tbits) bs32 += m;
+        else if (bits == tbits && band[tid].id != tok && m) tie_push(band[tid].id, m);
+      }
+      __syncthreads();
+      const int nt_ties = sc->c_n;
+      if (nt_ties > F_C_CAP) { if (tid == 0) hand_over(P, slow_ws, row, F_WHY_BUCKET); return; }
+      if (tid < nt_ties) {                                     // same truncated e as the token: original logit, then id
+        const float key = g[clist[tid].id] + 0.0f, tkey = g[tok] + 0.0f;
+        if (key > tkey || (key == tkey && clist[tid].id < tok)) bs32 += clist[tid].w;
+      }
+      u64 Qd = (u64)qs, Bd = (u64)bs32;
+      {                                                      // exact integer sums: any order
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          Qd += __shfl_xor_sync(0xffffffffu, Qd, o);
+          Bd += __shfl_xor_sync(0xffffffffu, Bd, o);
+        }
+        __syncthreads();
+        if ((tid & 31) == 0) { sc->red[tid >> 5] = Qd; sc->red[FW + (tid >> 5)] = Bd; }
+        __syncthreads();
+        Qd = 0; Bd = 0;
+#pragma unroll
+        for (int w = 0; w < FW; ++w) { Qd += sc->red[w]; Bd += sc->red[FW + w]; }
+      }
+      pc.mark(6);
+      if (Qd <= R) {
+        const u64 slack = R - Qd;                              // :158
+        const u64 top_mass = (u64)__double2ll_rn(C);           // e of the row maximum is exactly 1
+        bool in_range = tbits != 0u;
+        u64 ws = top_mass, bsum = 0;
+        int token = top_id;
+        if (in_range) {
+          uint32_t qt;
+          if (tok_in_band) { for (int k = 0; k < nband; ++k) if (band[k].id == tok) qt = (uint32_t)__double2ll_rn(band[k].e * C); }
+          else if (!quick_mass(e32t, &qt)) qt = exact_mass(tok);
+          ws = qt; bsum = Bd; token = tok;
+        }
+        u64 nb, nt;
+        if (token == top_id) { nb = lo; nt = lo + ws + slack; }   // :342 / :347-348
+        else { nb = lo + bsum + slack; nt = nb + ws; }
+        pc.mark(8);
+        if (tid == 0) finish_decode(P, row, slot, in_range, nb, nt, cand, Qd);
+        pc.mark(9);
+        return;
+      }
+      // overfill: the general path needs its lists empty again
+      __syncthreads();
+      if (tid == 0) { sc->u_n = 0; sc->c_n = 0; }
+      __syncthreads();
+    }
     // ------------------------------------------------------------------ P2: integer bin widths
     // two float4 per iteration: 8 independent conversion + FMA chains in flight per thread
     auto p2_slow = [&](const float4 v, const int b, const uint32_t* qv, const bool* kv) {
