@@ -57,7 +57,8 @@ struct CandEntry { uint32_t ebits; int id; uint32_t w; float key; };   // 16 B
 struct RowMeta {
   u64 lo, hi, window;
   int slot, cursor, mlen, tok;
-  int phase, pad;
+  int phase, olen;                   // decode: bits recovered so far
+  uint32_t oword, pad;               // decode: the partly filled output word at olen >> 5
 };
 
 struct FScal {
@@ -217,7 +218,7 @@ __device__ __forceinline__ RowMeta f_load_meta(const ns_ac_params& P, int row, i
   m.phase = P.phase ? (int)P.phase[row] : NS_PHASE_CODING;
   m.slot = P.ntok ? P.ntok[row] : 0;
   m.lo = P.lo[row]; m.hi = P.hi[row];
-  m.cursor = 0; m.mlen = 0; m.window = 0; m.tok = -1; m.pad = 0;
+  m.cursor = 0; m.mlen = 0; m.window = 0; m.tok = -1; m.pad = 0; m.olen = 0; m.oword = 0;
   if (mode == MODE_ENC) {
     m.cursor = P.cursor[row];
     m.mlen = P.msg_len[row];
@@ -226,8 +227,42 @@ __device__ __forceinline__ RowMeta f_load_meta(const ns_ac_params& P, int row, i
     const int total = P.ntok_total ? P.ntok_total[row] : 0x7fffffff;
     m.mlen = total;
     if (m.slot < total) m.tok = P.token_in[(size_t)row * P.token_stride + m.slot];
+    m.olen = P.out_len[row];
+    m.oword = P.out_bits[(size_t)row * P.out_stride + (m.olen >> 5)];
   }
   return m;
+}
+
+// finish_decode (ns_coder.cu) with the stream's scalars and its partly filled output word already in registers:
+// stores only, nothing on the row's path waits for global memory.  Needs ntok_total (else the caller uses
+// finish_decode).  Words past the partial one are fresh (the output buffer is append-only and zero-initialised).
+__device__ __forceinline__ void f_finish_decode(const ns_ac_params& P, int row, int slot, bool in_range, u64 nb, u64 nt,
+                                                u64 k0, u64 Q, int total, int olen, uint32_t oword) {
+  uint64_t nlo, nhi;
+  const int n = ns_interval_update(nb, nt, P.precision, &nlo, &nhi);
+  P.lo[row] = nlo; P.hi[row] = nhi;
+  const bool last = slot == total - 1;
+  if (P.ntok) P.ntok[row] = slot + 1;
+  if (P.phase && slot + 1 >= total) P.phase[row] = NS_PHASE_DONE;
+  const int count = last ? P.precision : n;                  // :356-359
+  const u64 value = last ? nb : (n > 0 ? (nt - 1) >> (P.precision - n) : 0ull);
+  uint32_t* ob = P.out_bits + (size_t)row * P.out_stride;
+  int done = 0;
+  uint32_t w = oword;
+  while (done < count) {
+    const int b = olen + done, off = b & 31;
+    int chunk = 32 - off;
+    if (chunk > count - done) chunk = count - done;
+    const uint32_t mask = chunk == 32 ? 0xFFFFFFFFu : ((1u << chunk) - 1u);
+    const uint32_t part = (uint32_t)(value >> (count - done - chunk)) & mask;
+    ob[b >> 5] = w | (part << (32 - off - chunk));
+    w = 0;
+    done += chunk;
+  }
+  P.out_len[row] = olen + count;
+  if (P.nbits_out) P.nbits_out[row] = (uint8_t)n;
+  if (!in_range && P.status) atomicOr(&P.status[row], NS_ST_OUT_OF_RANGE);
+  if (P.trace) { uint64_t* t = P.trace + (size_t)row * 4; t[0] = nb; t[1] = nt; t[2] = k0; t[3] = Q; }
 }
 
 // phase timers (thread 0 only, active when P.prof is given)
@@ -1069,7 +1104,10 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
         if (token == top_id) { nb = lo; nt = lo + ws + slack; }   // :342 / :347-348
         else { nb = lo + bsum + slack; nt = nb + ws; }
         pc.mark(8);
-        if (tid == 0) finish_decode(P, row, slot, in_range, nb, nt, cand, Qd);
+        if (tid == 0) {
+          if (P.ntok_total) f_finish_decode(P, row, slot, in_range, nb, nt, cand, Qd, meta.mlen, meta.olen, meta.oword);
+          else finish_decode(P, row, slot, in_range, nb, nt, cand, Qd);
+        }
         pc.mark(9);
         return;
       }
