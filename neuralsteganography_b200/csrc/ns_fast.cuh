@@ -67,6 +67,7 @@ struct FScal {
   u64 bar[F_PIECES];                 // mbarriers of the row copy
   float sum32; int remax; float M; int top_id;
   int band_n; int u_n; int c_n; int bail;
+  int issued_row; int pad_issue;     // row whose bulk copy is already in flight (issued before the previous row ended)
   u64 band_cut_int;
   int band_kept_n; int sh;
   int sel_bin; u64 sel_prefix;
@@ -108,6 +109,13 @@ __device__ __forceinline__ void f_mbar_wait(u64* bar, uint32_t parity) {
       "DONE_%=:\n\t"
       "}\n" :: "r"(f_smem_addr(bar)), "r"(parity) : "memory");
 }
+
+#if !NSF_STREAM
+// Bulk copy of row `row` into the shared-memory row (interior float4 chunks 1 .. W4-2, F_PIECES pieces, one
+// mbarrier each).  One thread.  Every generic-proxy access of the buffer's previous content must be behind a
+// CTA barrier; the proxy fence orders them before the async-proxy writes.
+__device__ __forceinline__ void f_issue_row(const ns_ac_params& P, int row, u64* bar, float* words, int* issued_row);
+#endif
 
 // The exp pass leaves, in place of each kept logit, a 32-bit truncation of its fp64 e: the double's
 // bits 59..28 (low 8 exponent bits + 24 mantissa bits; for 2^-255 < e <= 1 the four bits above are the
@@ -207,6 +215,28 @@ __device__ __forceinline__ void f_sum_ddu(double& a, double& b, u64& c, u64* scr
   }
   a = ra; b = rb; c = rc;
 }
+
+#if !NSF_STREAM
+__device__ __forceinline__ void f_issue_row(const ns_ac_params& P, int row, u64* bar, float* words, int* issued_row) {
+  const float* g = P.logits + (size_t)row * (size_t)P.ld;
+  const int mis = (int)(((uintptr_t)g & 15u) >> 2);
+  const int NI = ((mis + P.V + 3) >> 2) - 2;
+  constexpr int PC = 3 * NSF_FT;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  const char* src = reinterpret_cast<const char*>(g - mis) + 16;
+  char* dst = reinterpret_cast<char*>(words) + 16;
+  for (int k = 0; k < 9; ++k) {
+    const int c0 = k * PC;
+    int n = NI - c0;
+    if (n > PC) n = PC;
+    if (n > 0) {
+      f_mbar_expect_tx(&bar[k], (uint32_t)n * 16u);
+      f_bulk_g2s(dst + (size_t)c0 * 16, src + (size_t)c0 * 16, (uint32_t)n * 16u, &bar[k]);
+    }
+  }
+  *issued_row = row;
+}
+#endif
 
 struct FastSmem {
   double* tab; uint32_t* hist; BandEntry* band; int* ulist; CandEntry* clist; FScal* sc; float* words;
@@ -444,6 +474,10 @@ __device__ __noinline__ int fast_rank_row(const ns_ac_params& P, int32_t* slow_w
     }
   }
   __syncthreads();
+  {   // the shared-memory row is not read again: the next row's bulk copy starts now, behind the rest of this row
+    const int nrow = row + (int)gridDim.x;
+    if (tid == 0 && nrow < P.B) f_issue_row(P, nrow, sc->bar, const_cast<float*>(words), &sc->issued_row);
+  }
   {
     uint32_t excl, total2;
     scan_hist(&excl, &total2);
@@ -614,8 +648,27 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
   const double temp = P.temp;
   const float c2 = (float)(1.4426950408889634 / temp);     // log2(e)/temp for the fp32 estimate
   const double magic = 6755399441055744.0;                 // 1.5 * 2^52
+  // Called by every thread right after a CTA barrier that follows the row's last access to the shared-memory
+  // row: thread 0 starts the next row's bulk copy, whose latency then overlaps the rest of this row.
+  auto next_row_copy = [&]() {
+#if !NSF_STREAM
+    const int nrow = row + (int)gridDim.x;
+    if (tid == 0 && nrow < P.B) f_issue_row(P, nrow, sc->bar, words, &sc->issued_row);
+#endif
+  };
   int phase = meta.phase;
-  if (phase == NS_PHASE_DONE) return;
+  // a row that is skipped still has to consume its bulk copy if the previous row already started it
+  auto drain = [&]() {
+#if !NSF_STREAM
+    if (sc->issued_row == row) {
+      const float* g0 = P.logits + (size_t)row * (size_t)P.ld;
+      const int NI0 = ((((int)(((uintptr_t)g0 & 15u) >> 2)) + V + 3) >> 2) - 2;
+      for (int k = 0; k < F_PIECES; ++k)
+        if (NI0 - k * 3 * FT > 0) { f_mbar_wait(&sc->bar[k], (parity >> k) & 1u); parity ^= (1u << k); }
+    }
+#endif
+  };
+  if (phase == NS_PHASE_DONE) { drain(); return; }
   if (MODE != MODE_ENC) phase = NS_PHASE_CODING;
   const int slot = meta.slot;
   {
@@ -624,10 +677,12 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
         if (P.phase) P.phase[row] = NS_PHASE_DONE;
         if (P.status) atomicOr(&P.status[row], NS_ST_TOKEN_OVERFLOW);
       }
+      drain();
       return;
     }
     if (MODE == MODE_DEC && P.ntok_total && slot >= meta.mlen) {
       if (tid == 0 && P.phase) P.phase[row] = NS_PHASE_DONE;
+      drain();
       return;
     }
 
@@ -670,19 +725,8 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     };
 #else
     if (tid == 0) {
-      // generic-proxy accesses of the previous row are ordered before the async-proxy writes
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      const char* src = reinterpret_cast<const char*>(g - mis) + 16;
-      char* dst = reinterpret_cast<char*>(w4 + 1);
-      for (int k = 0; k < F_PIECES; ++k) {
-        const int c0 = k * PC;
-        int n = NI - c0;
-        if (n > PC) n = PC;
-        if (n > 0) {
-          f_mbar_expect_tx(&sc->bar[k], (uint32_t)n * 16u);
-          f_bulk_g2s(dst + (size_t)c0 * 16, src + (size_t)c0 * 16, (uint32_t)n * 16u, &sc->bar[k]);
-        }
-      }
+      // (unless the previous row already started this copy once it was done with the buffer)
+      if (sc->issued_row != row) f_issue_row(P, row, sc->bar, words, &sc->issued_row);
       sc->band_n = 0; sc->u_n = 0; sc->c_n = 0; sc->bail = 0; sc->band_cut_int = 0; sc->remax = 0; sc->band_kept_n = 0;
     }
     // the two edge chunks may straddle the row ends: plain loads, -inf padding
@@ -697,11 +741,26 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     for (int i = tid; i < F_NB / 4; i += FT) reinterpret_cast<uint4*>(hist)[i] = make_uint4(0, 0, 0, 0);
     {   // prefetch this CTA's next row into L2 while this one is processed
       const int nrow = row + gridDim.x;
+#if NSF_STREAM
       if (nrow < P.B) {
         const char* np = reinterpret_cast<const char*>(P.logits + (size_t)nrow * (size_t)P.ld);
         const int nbytes = V * 4;
         for (int off = tid * 128; off < nbytes; off += FT * 128) f_prefetch_l2(np + off);
       }
+#else
+      // one bulk prefetch per warp leader: the copy engine walks the lines.  Per-lane prefetch instructions
+      // (32 lines each) occupy the load/store pipe for ~1.5k cycles and hold back the estimate's shared loads.
+      if (nrow < P.B && (tid & 31) == 0) {
+        const char* np = reinterpret_cast<const char*>(P.logits + (size_t)nrow * (size_t)P.ld);
+        const char* a0 = reinterpret_cast<const char*>(((uintptr_t)np + 15u) & ~(uintptr_t)15u);
+        const int nbytes = (int)(np + (size_t)V * 4 - a0) & ~15;
+        const int per = ((nbytes / FW) + 15) & ~15;
+        const int o = (tid >> 5) * per;
+        int n = nbytes - o;
+        if (n > per) n = per;
+        if (n > 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a0 + o), "r"(n) : "memory");
+      }
+#endif
     }
     pc.mark(0);                                            // row prologue: copy issue, edges, prefetch
     // fp32 online softmax over the pieces as they land: (tm, ts) per thread, lowest id of the max
@@ -1089,6 +1148,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       }
       pc.mark(6);
       if (Qd <= R) {
+        next_row_copy();                                       // the row buffer is not read again
         const u64 slack = R - Qd;                              // :158
         const u64 top_mass = (u64)__double2ll_rn(C);           // e of the row maximum is exactly 1
         bool in_range = tbits != 0u;
@@ -1288,12 +1348,14 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       return sc->res_found != 0;
     };
     bool overflow = false;                                   // a gathered bucket did not fit (uniform across the CTA)
-    auto select_tau = [&](u64 tau, int* idx, u64* before, u64* w) -> bool {
+    // `last`: nothing reads the shared-memory row after this selection's gather
+    auto select_tau = [&](u64 tau, int* idx, u64* before, u64* w, bool last) -> bool {
       locate(tau);
       const int tb = sc->sel_bin;
       const u64 pref = sc->sel_prefix;
-      if (tb < 0) return false;
+      if (tb < 0) { if (last) next_row_copy(); return false; }
       const int n = collect(tb);
+      if (last) next_row_copy();
       if (n < 0) { overflow = true; return false; }
       const bool f = resolve(n, pref, false, tau, 0);
       *idx = sc->res_idx; *before = sc->res_before; *w = sc->res_w;
@@ -1307,7 +1369,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     CandEntry trunc_e = {0u, 0, 0u, 0.0f};
     if (Q > R) {
       int j; u64 bj, wj;
-      if (select_tau(R, &j, &bj, &wj)) {
+      if (select_tau(R, &j, &bj, &wj, false)) {
         truncated = true;
         trunc_e.ebits = __float_as_uint(word_ld1(j + mis));
         for (int k = 0; k < nband; ++k) if (band[k].id == j) trunc_e.ebits = __float_as_uint(f_pack_e(band[k].e));
@@ -1325,10 +1387,11 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       const u64 m_rel = meta.window - lo;                    // next `precision` message bits (:168-171)
       int token;
       if (m_rel < top_mass + slack) {                        // rank 0 absorbs the slack (:158)
+        next_row_copy();
         token = top_id; nb = lo; nt = lo + top_mass + slack;
       } else {
         int s; u64 bs, ws;
-        if (!select_tau(m_rel - slack, &s, &bs, &ws)) {
+        if (!select_tau(m_rel - slack, &s, &bs, &ws, true)) {
           if (overflow) { if (tid == 0) hand_over(P, slow_ws, row, F_WHY_BUCKET); return; }
           s = top_id; bs = 0; ws = top_mass;
           if (tid == 0 && P.status) atomicOr(&P.status[row], NS_ST_BIN_OVERFLOW);
@@ -1400,6 +1463,7 @@ __global__ void __launch_bounds__(FT, NSF_MIN_CTAS) ac_fast_kernel(const __grid_
   if (tid == 0) {
     for (int k = 0; k < F_PIECES; ++k) f_mbar_init(&sm.sc->bar[k], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    sm.sc->issued_row = -1;
   }
 #endif
   if (tid == HELPER && (int)blockIdx.x < P.B) sm.sc->meta[0] = f_load_meta(P, blockIdx.x, MODE);
