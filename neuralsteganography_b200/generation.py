@@ -22,10 +22,10 @@ class StegoGenerator:
     def __init__(self, hf_model, batch: int, *, max_len: int = 256, precision: int = 16, temp: float = 1.0,
                  topk: int = 50000, finish_sent: bool = False, sent_end: Optional[torch.Tensor] = None,
                  device="cuda", use_graph: bool = True, trunk_dtype: torch.dtype = torch.float32,
-                 collect_stats: bool = False):
+                 collect_stats: bool = False, trunk_tf32: bool = False):
         self.B = int(batch)
         self.device = torch.device(device)
-        self.trunk = StaticGPT2(hf_model, batch, max_len=max_len, device=device, dtype=trunk_dtype)
+        self.trunk = StaticGPT2(hf_model, batch, max_len=max_len, device=device, dtype=trunk_dtype, tf32=trunk_tf32)
         self.V = self.trunk.vocab
         self.max_len = int(max_len)
         self.kw = dict(precision=precision, temp=temp, topk=topk, finish_sent=finish_sent, sent_end=sent_end)

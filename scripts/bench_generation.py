@@ -9,13 +9,14 @@ import numpy as np
 
 B = int(os.environ.get("STREAMS", "256"))
 BITS = int(os.environ.get("BITS", "1024"))
-dtype = {"fp32": torch.float32, "bf16": torch.bfloat16}[os.environ.get("TRUNK", "fp32")]
+dtype = {"fp32": torch.float32, "tf32": torch.float32, "bf16": torch.bfloat16}[os.environ.get("TRUNK", "fp32")]
+tf32 = os.environ.get("TRUNK", "fp32") == "tf32"
 _tok, model = random_init_model("gpt2")
 model = model.cuda()
 ctx = torch.tensor([50256, 11, 22])
 msgs = [np.random.default_rng(10 + r).integers(0, 2, BITS).tolist() for r in range(B)]
 for graph in (True, False):
-    gen = StegoGenerator(model, B, max_len=512, precision=26, temp=0.9, topk=300, use_graph=graph, trunk_dtype=dtype)
+    gen = StegoGenerator(model, B, max_len=512, precision=26, temp=0.9, topk=300, use_graph=graph, trunk_dtype=dtype, trunk_tf32=tf32)
     gen.encode(ctx, msgs, poll_every=32)            # warm-up (builds, captures)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
