@@ -908,7 +908,8 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     if (tid == 0) {
       const double theta_est = thr * (double)ssum;
       int bail = !(ssum > 0.0f) || !(R >= 2);
-      const double a_th = log(theta_est);
+      // fp32 log2 is plenty: the band around the cutoff absorbs the error and the split is verified exactly
+      const double a_th = (double)(0.6931471805599453f * __log2f((float)theta_est));
       const double key_th = Md + temp * a_th;
       sc->kappa_hi = (float)(key_th + temp * (double)F_BAND_EPS);
       sc->kappa_lo = (float)(key_th - temp * (double)F_BAND_EPS);
