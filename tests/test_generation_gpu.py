@@ -123,3 +123,25 @@ def test_generation_slides_the_1022_token_window():
         rows.append(tr.step(torch.tensor([t], device="cuda"), tr.kv_bucket(len(ctx) + s + 1))[0].cpu().numpy())
     res = O.encode_stream(lambda t: rows[t], msgs[0], temp=1.0, precision=16, topk=2048, max_steps=len(rows))
     assert res.tokens == toks[0]
+
+
+def test_config4_shape_batched_decode_recovers_every_message():
+    """BASELINE config 4: gpt2-fa-shaped random-init trunk (42001 tokens, 12 layers x 768), 1024 streams, cover
+    produced by our own encode, then the batched decode path recovers every message from the cover token ids."""
+    from neuralsteganography_b200.generation import StegoGenerator
+    from neuralsteganography_b200.lm import random_init_model
+    _tok, model = random_init_model("gpt2-fa")
+    model = model.cuda()
+    B, bits = 1024, 768
+    gen = StegoGenerator(model, B, max_len=320, precision=26, temp=0.9, topk=300, use_graph=True)
+    assert gen.V == 42001
+    ctx = torch.tensor([5, 11, 22])
+    rng = np.random.default_rng(44)
+    msgs = [rng.integers(0, 2, bits - 8 * (r % 5)).tolist() for r in range(B)]
+    toks = gen.encode(ctx, msgs, poll_every=16)
+    assert gen.coder.all_done()
+    assert int((gen.coder.status & 0xB).sum().item()) == 0
+    assert max(len(t) for t in toks) <= 256
+    got = gen.decode(ctx, toks, poll_every=16)
+    for r in range(B):
+        assert got[r][: len(msgs[r])] == msgs[r], r
