@@ -460,22 +460,34 @@ __global__ void __launch_bounds__(NT, 1) huffman_kernel(ns_codec_params P) {
   int n = 1 << P.param;                                      // top 2^bits_per_word options, :30
   if (n > V) n = V;
   // log_softmax over the whole row (:32), accumulated in double like torch's CPU kernel
+  // (the same sweep fills the count histogram of the selection: staging left it zeroed)
   double acc = 0.0;
-  for (int i = tid; i < V; i += NT) acc += (double)expf(keys[i] - m);
+  {
+    constexpr int NB = HIST_BYTES / 4;
+    const float span = m - key_of_pack(pmin);
+    const float scale = span > 0.0f ? (float)NB / span : 0.0f;
+    for (int i = tid; i < V; i += NT) {
+      const float k = keys[i];
+      acc += (double)expf(k - m);
+      atomicAdd(&sm.hist[bin_of(k, m, scale, NB)], 1u);
+    }
+  }
   __syncthreads();
   const double sum = block_sum_d(acc, sm.sc->red);
   const float lse = (float)log(sum);
   // the n-th element of the order bounds the kept set
-  const int bound_id = element_at(keys, V, pmax, pmin, (u64)(n - 1), sm, P.status ? &P.status[row] : nullptr);
+  const int bound_id = element_from_hist(keys, V, pmax, pmin, (u64)(n - 1), sm, P.status ? &P.status[row] : nullptr);
   const u64 bound = bound_id >= 0 ? pack_of(keys[bound_id], bound_id) : pmin;
+  const float bkey = key_of_pack(bound);
+  const int bid = id_of_pack(bound);
   __syncthreads();
   if (tid == 0) sm.sc->list_count = 0;
   __syncthreads();
   for (int i = tid; i < V; i += NT) {
-    const u64 p = pack_of(keys[i], i);
-    if (p >= bound) {
+    const float k = keys[i];
+    if (k > bkey || (k == bkey && i <= bid)) {               // pack_of(k, i) >= bound (keys are -0-free)
       const int s = atomicAdd(&sm.sc->list_count, 1);
-      if (s < CODEC_LIST_CAP) { sm.list[s].pack = p; sm.list[s].w = 0; }
+      if (s < CODEC_LIST_CAP) { sm.list[s].pack = pack_of(k, i); sm.list[s].w = 0; }
     }
   }
   __syncthreads();
