@@ -842,57 +842,129 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
         if (v.w > -INFINITY) kmin = fminf(kmin, v.w);
       }
     }
-    u64 pmax = pack_of(tm + 0.0f, ti), pmin_k = pack_of(kmin, 0);
-    f_reduce_maxmin(pmax, pmin_k, sc->red);
-    float M = key_of_pack(pmax);
-    int top_id = id_of_pack(pmax);
-    float ssum = f_sum_f(ts * f_ex2((tm - M) * c2), sc->red);
-    // lowest interior logit (-inf if the caller masked tokens with -inf: then the cutoff bounds the range)
-    const float key_min = key_of_pack(pmin_k);
-    // forbidden tokens (code_base/arithmetic.py:124-125): probability exactly 0
-    if (tid == 0) {
-      int remax = 0;
+    float M, ssum, key_min;
+    int top_id;
+    if (RANK) {
+      // Row reductions with one barrier (the instantiation that carries the rank form, where no fp64 pass follows;
+      // in the threshold-only kernel this form makes the exp pass's code slower by more than it saves): warp partials
+      // (max key with its lowest id, the sum rescaled to the warp's max, the lowest key) meet in shared memory, then
+      // every warp combines the FW partials the same way -- identical bits in every thread, no broadcast.
+      float xmask[2] = {-INFINITY, -INFINITY};             // raw logits of the forbidden tokens (estimate's correction)
+      const int lane = tid & 31, warp = tid >> 5;
+      const uint32_t ok = ns_f32_orderable(tm + 0.0f);
+      const uint32_t wk = __reduce_max_sync(0xffffffffu, ok);
+      const int wi = __reduce_min_sync(0xffffffffu, ok == wk ? ti : 0x7fffffff);
+      const float wm = key_of_pack((u64)wk << 32);
+      float wts = ts * f_ex2((tm - wm) * c2);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) wts += __shfl_xor_sync(0xffffffffu, wts, o);
+      const uint32_t wmin = __reduce_min_sync(0xffffffffu, ns_f32_orderable(kmin));
+      uint4* red4 = reinterpret_cast<uint4*>(sc->red);
+      if (lane == 0) red4[warp] = make_uint4(wk, (uint32_t)wi, __float_as_uint(wts), wmin);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int id = P.mask_id[k];
+        if (id >= 0 && id < V) xmask[k] = NSF_STREAM ? g[id] : words[id + mis];
+      }
+      __syncthreads();
+      const uint4 pr = red4[lane < FW ? lane : 0];
+      const uint32_t mk = __reduce_max_sync(0xffffffffu, pr.x);
+      top_id = __reduce_min_sync(0xffffffffu, pr.x == mk ? (int)pr.y : 0x7fffffff);
+      M = key_of_pack((u64)mk << 32);
+      key_min = key_of_pack((u64)__reduce_min_sync(0xffffffffu, pr.w) << 32);
+      float part = lane < FW ? __uint_as_float(pr.z) * f_ex2((key_of_pack((u64)pr.x << 32) - M) * c2) : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      ssum = part;
+      // forbidden tokens (code_base/arithmetic.py:124-125): probability exactly 0
+      bool remax = false;
+#pragma unroll
       for (int k = 0; k < 2; ++k) {
         const int id = P.mask_id[k];
         if (id >= 0 && id < V) {
-#if NSF_STREAM
-          const float x = g[id];
-          if (x > -INFINITY) ssum -= f_ex2((x - M) * c2);
-#else
-          const float x = words[id + mis];
-          if (x > -INFINITY) { ssum -= f_ex2((x - M) * c2); words[id + mis] = -INFINITY; }
+          if (xmask[k] > -INFINITY) ssum -= f_ex2((xmask[k] - M) * c2);
+          if (id == top_id) remax = true;
+#if !NSF_STREAM
+          if (tid == k) words[id + mis] = -INFINITY;
 #endif
-          if (id == top_id) remax = 1;
         }
       }
-      sc->remax = remax;
-      sc->sum32 = ssum;
-    }
-    __syncthreads();
-    if (sc->remax) {                                       // rare: the row maximum itself was forbidden
-      u64 pm = 0;
-      for (int c = tid; c < W4; c += FT) {
-        const float4 v = raw4_p(c);
-        const int b = 4 * c - mis;
-        u64 p;
-        p = pack_of(v.x + 0.0f, b); pm = p > pm ? p : pm;
-        p = pack_of(v.y + 0.0f, b + 1); pm = p > pm ? p : pm;
-        p = pack_of(v.z + 0.0f, b + 2); pm = p > pm ? p : pm;
-        p = pack_of(v.w + 0.0f, b + 3); pm = p > pm ? p : pm;
+      __syncthreads();                                     // the -inf is visible to whoever sweeps the row next
+      if (remax) {                                         // rare: the row maximum itself was forbidden
+        u64 pm = 0;
+        for (int c = tid; c < W4; c += FT) {
+          const float4 v = raw4_p(c);
+          const int b = 4 * c - mis;
+          u64 p;
+          p = pack_of(v.x + 0.0f, b); pm = p > pm ? p : pm;
+          p = pack_of(v.y + 0.0f, b + 1); pm = p > pm ? p : pm;
+          p = pack_of(v.z + 0.0f, b + 2); pm = p > pm ? p : pm;
+          p = pack_of(v.w + 0.0f, b + 3); pm = p > pm ? p : pm;
+        }
+        pm = f_reduce_u(pm, OpMaxU(), sc->red);
+        M = key_of_pack(pm);
+        top_id = id_of_pack(pm);
+        float s = 0.f;
+        for (int c = tid; c < W4; c += FT) {
+          const float4 v = raw4_p(c);
+          s += f_ex2((v.x - M) * c2) + f_ex2((v.y - M) * c2) + f_ex2((v.z - M) * c2) + f_ex2((v.w - M) * c2);
+        }
+        ssum = f_sum_f(s, sc->red);
       }
-      pm = f_reduce_u(pm, OpMaxU(), sc->red);
-      M = key_of_pack(pm);
-      top_id = id_of_pack(pm);
-      float s = 0.f;
-      for (int c = tid; c < W4; c += FT) {
-        const float4 v = raw4_p(c);
-        s += f_ex2((v.x - M) * c2) + f_ex2((v.y - M) * c2) + f_ex2((v.z - M) * c2) + f_ex2((v.w - M) * c2);
+    } else {
+      u64 pmax = pack_of(tm + 0.0f, ti), pmin_k = pack_of(kmin, 0);
+      f_reduce_maxmin(pmax, pmin_k, sc->red);
+      M = key_of_pack(pmax);
+      top_id = id_of_pack(pmax);
+      ssum = f_sum_f(ts * f_ex2((tm - M) * c2), sc->red);
+      // lowest interior logit (-inf if the caller masked tokens with -inf: then the cutoff bounds the range)
+      key_min = key_of_pack(pmin_k);
+      // forbidden tokens (code_base/arithmetic.py:124-125): probability exactly 0
+      if (tid == 0) {
+        int remax = 0;
+        for (int k = 0; k < 2; ++k) {
+          const int id = P.mask_id[k];
+          if (id >= 0 && id < V) {
+  #if NSF_STREAM
+            const float x = g[id];
+            if (x > -INFINITY) ssum -= f_ex2((x - M) * c2);
+  #else
+            const float x = words[id + mis];
+            if (x > -INFINITY) { ssum -= f_ex2((x - M) * c2); words[id + mis] = -INFINITY; }
+  #endif
+            if (id == top_id) remax = 1;
+          }
+        }
+        sc->remax = remax;
+        sc->sum32 = ssum;
       }
-      s = f_sum_f(s, sc->red);
-      if (tid == 0) sc->sum32 = s;
       __syncthreads();
+      if (sc->remax) {                                       // rare: the row maximum itself was forbidden
+        u64 pm = 0;
+        for (int c = tid; c < W4; c += FT) {
+          const float4 v = raw4_p(c);
+          const int b = 4 * c - mis;
+          u64 p;
+          p = pack_of(v.x + 0.0f, b); pm = p > pm ? p : pm;
+          p = pack_of(v.y + 0.0f, b + 1); pm = p > pm ? p : pm;
+          p = pack_of(v.z + 0.0f, b + 2); pm = p > pm ? p : pm;
+          p = pack_of(v.w + 0.0f, b + 3); pm = p > pm ? p : pm;
+        }
+        pm = f_reduce_u(pm, OpMaxU(), sc->red);
+        M = key_of_pack(pm);
+        top_id = id_of_pack(pm);
+        float s = 0.f;
+        for (int c = tid; c < W4; c += FT) {
+          const float4 v = raw4_p(c);
+          s += f_ex2((v.x - M) * c2) + f_ex2((v.y - M) * c2) + f_ex2((v.z - M) * c2) + f_ex2((v.w - M) * c2);
+        }
+        s = f_sum_f(s, sc->red);
+        if (tid == 0) sc->sum32 = s;
+        __syncthreads();
+      }
+      ssum = sc->sum32;
+
     }
-    ssum = sc->sum32;
 
     if (MODE == MODE_ENC && phase == NS_PHASE_TAIL) {
       if (tid == 0) finish_tail(P, row, slot, top_id);
@@ -905,22 +977,37 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     const double thr = __ddiv_rn(1.0, (double)R);            // :141
     const double Md = (double)M;
     const double dm = UNIT_TEMP ? Md : __ddiv_rn(Md, temp);
-    if (tid == 0) {
+    // provisional cutoff from the fp32 estimate: p >= 1/R  <=>  key >= M + temp * ln(sum / R).  fp32 log2 is plenty:
+    // the band around the cutoff (F_BAND_EPS) absorbs the error and the split is verified exactly after the exp pass
+    float kappa_hi, kappa_lo, clamp_key;
+    if (RANK) {                                              // every thread, same bits: no broadcast, no barrier
       const double theta_est = thr * (double)ssum;
-      int bail = !(ssum > 0.0f) || !(R >= 2);
-      // fp32 log2 is plenty: the band around the cutoff absorbs the error and the split is verified exactly
-      const double a_th = (double)(0.6931471805599453f * __log2f((float)theta_est));
-      const double key_th = Md + temp * a_th;
-      sc->kappa_hi = (float)(key_th + temp * (double)F_BAND_EPS);
-      sc->kappa_lo = (float)(key_th - temp * (double)F_BAND_EPS);
-      sc->clamp_key = (float)(Md - 700.0 * temp);
-      sc->band_E = ilogb(theta_est) - 1;
-      if (!(sc->kappa_lo > sc->clamp_key)) bail = 1;
-      sc->bail = bail;
+      const float tf = (float)temp;
+      const float key_th = fmaf(tf * 0.6931471805599453f, __log2f((float)theta_est), M);
+      kappa_hi = key_th + tf * F_BAND_EPS; kappa_lo = key_th - tf * F_BAND_EPS;
+      clamp_key = (float)(Md - 700.0 * temp);
+      if (tid == 0) sc->band_E = ((__double2hiint(theta_est) >> 20) & 0x7ff) - 1024;   // ilogb(theta_est) - 1; read after barriers
+      if (!(ssum > 0.0f) || !(R >= 2) || !(kappa_lo > clamp_key)) {
+        if (tid == 0) hand_over(P, slow_ws, row, F_WHY_EST);
+        return;
+      }
+    } else {
+      if (tid == 0) {
+        const double theta_est = thr * (double)ssum;
+        int bail = !(ssum > 0.0f) || !(R >= 2);
+        const double a_th = (double)(0.6931471805599453f * __log2f((float)theta_est));
+        const double key_th = Md + temp * a_th;
+        sc->kappa_hi = (float)(key_th + temp * (double)F_BAND_EPS);
+        sc->kappa_lo = (float)(key_th - temp * (double)F_BAND_EPS);
+        sc->clamp_key = (float)(Md - 700.0 * temp);
+        sc->band_E = ilogb(theta_est) - 1;
+        if (!(sc->kappa_lo > sc->clamp_key)) bail = 1;
+        sc->bail = bail;
+      }
+      __syncthreads();
+      if (sc->bail) { if (tid == 0) hand_over(P, slow_ws, row, F_WHY_EST); return; }
+      kappa_hi = sc->kappa_hi; kappa_lo = sc->kappa_lo; clamp_key = sc->clamp_key;
     }
-    __syncthreads();
-    if (sc->bail) { if (tid == 0) hand_over(P, slow_ws, row, F_WHY_EST); return; }
-    const float kappa_hi = sc->kappa_hi, kappa_lo = sc->kappa_lo, clamp_key = sc->clamp_key;
 
     auto a_of = [&](float key) -> double {                  // (double(x)/temp) - (double(max)/temp), :128-130
       double x = (double)fmaxf(key, clamp_key);
