@@ -1,10 +1,11 @@
 // ns_fast.cuh -- single-exp-pass arithmetic-coder step (the throughput path), sm_100a.
 // Included by ns_coder.cu after the shared definitions (u64, pack_of, finish_*).
 //
-// Persistent CTAs (one per SM, 512 threads), each looping over rows.  Per row:
-//   L   the row is pulled into shared memory by the bulk-copy engine (cp.async.bulk, 8 pieces, one
-//       mbarrier each); while pieces land, an fp32 online softmax estimate (row max, its lowest id,
-//       sum of exp) runs over the pieces already there.  The CTA's next row is prefetched into L2.
+// Persistent CTAs (one per SM, 512 threads), each looping over rows.  Per row (threshold form of the cutoff):
+//   L   the row is pulled into shared memory by the bulk-copy engine (cp.async.bulk, 9 pieces, one
+//       mbarrier each) -- issued by the previous row as soon as that row has read the buffer for the last
+//       time; while pieces land, an fp32 online softmax estimate (row max, its lowest id, sum of exp) runs
+//       over the pieces already there.  The row after this one is prefetched into L2 (bulk prefetch).
 //   P1  ONE fp64 exp per element (10 fp64 ops): exact sum of all e_i in a fixed order, exact sum of
 //       the provisionally-cut ones, elements within 2^-10 of the provisional cutoff go to a small
 //       list with their exact e ; the word is overwritten in place by the high word of e_i (0 if not kept)
@@ -12,12 +13,15 @@
 //       S_kept and C = range / S_kept exact
 //   P2  q_i = rint(e_i * C) from the truncated e_i with a rigorous interval test (2 fp64 FMAs);
 //       the few undecidable ones are redone exactly from the original logit (L2 hit) ;
-//       integer mass histogram over 2048 monotone buckets of the fp32 bit pattern
-//   SEL bucket prefix -> gather the target bucket -> exact order (e32, then original logit, then id)
+//       encode: integer mass histogram over 2048 monotone buckets of the fp32 bit pattern;
+//       decode: no histogram -- the mass ranked before the observed token is a conditional sum
+//   SEL (encode) bucket prefix -> gather the target bucket -> exact order (e32, original logit, id)
 //   UPD shared-prefix bits + interval rescale (finish_encode / finish_decode)
-// Anything unusual (top-k smaller than the cutoff set, list overflow, estimate outside its guard
-// band) queues the row in slow_ws; the exact multi-pass kernel then redoes it.  The decision only
-// depends on the row and its range, never on encode/decode, so both directions take the same path.
+// Rank form (top-k binds, 2 <= topk <= 512; fast_rank_row, RANK instantiation): after L, no fp64 pass over the
+// row -- sampled histogram -> bound on the top-k key -> candidate list -> exact selection of the topk keys ->
+// exp / widths / prefix sums on topk elements.
+// Anything unusual (list overflows, estimate outside its guard band, rank form beyond the lists) queues
+// the row in slow_ws; the exact multi-pass kernel then redoes it with the same integers.
 
 // This header is compiled twice (ns_coder.cu), each time inside its own namespace:
 //   NSF_STREAM 0  one CTA per SM, 512 threads, the row resident in shared memory (bulk copy);
