@@ -2,10 +2,9 @@
 // Included by ns_coder.cu after the shared definitions (u64, pack_of, finish_*).
 //
 // Persistent CTAs (one per SM, 512 threads), each looping over rows.  Per row (threshold form of the cutoff):
-//   L   the row is pulled into shared memory by the bulk-copy engine (cp.async.bulk, 9 pieces, one
-//       mbarrier each) -- issued by the previous row as soon as that row has read the buffer for the last
-//       time; while pieces land, an fp32 online softmax estimate (row max, its lowest id, sum of exp) runs
-//       over the pieces already there.  The row after this one is prefetched into L2 (bulk prefetch).
+//   L   the row is pulled into shared memory by the bulk-copy engine (cp.async.bulk, one copy, one
+//       mbarrier) -- issued by the previous row as soon as that row has read the buffer for the last
+//       time; then an fp32 online softmax estimate (row max, its lowest id, sum of exp) runs over it.  The row after this one is prefetched into L2 (bulk prefetch).
 //   P1  ONE fp64 exp per element (10 fp64 ops): exact sum of all e_i in a fixed order, exact sum of
 //       the provisionally-cut ones, elements within 2^-10 of the provisional cutoff go to a small
 //       list with their exact e ; the word is overwritten in place by the high word of e_i (0 if not kept)
@@ -46,7 +45,8 @@ constexpr int F_BPT = F_NB / FT;     // buckets per thread in the scan
 constexpr int F_BAND_CAP = 128;
 constexpr int F_U_CAP = 256;
 constexpr int F_C_CAP = 256;
-constexpr int F_PIECES = 9;          // bulk-copy pieces per row (3 * FT float4 each, 24 KB)
+constexpr int F_PIECES = 1;          // bulk-copy pieces per row (F_SUB * 3 * FT float4 each)
+constexpr int F_SUB = 9;             // blocks of 3 float4 per thread in a piece
 constexpr int F_MIN_VOCAB = 256;     // below this the exact kernel is used
 constexpr float F_BAND_EPS = 0.0009765625f;   // 2^-10 half-width (in log units) of the exact-list band
 constexpr uint32_t F_TOP = 0xFF000000u;       // packed e of the row maximum (e == 1.0)
@@ -225,11 +225,11 @@ __device__ __forceinline__ void f_issue_row(const ns_ac_params& P, int row, u64*
   const float* g = P.logits + (size_t)row * (size_t)P.ld;
   const int mis = (int)(((uintptr_t)g & 15u) >> 2);
   const int NI = ((mis + P.V + 3) >> 2) - 2;
-  constexpr int PC = 3 * NSF_FT;
+  constexpr int PC = F_SUB * 3 * NSF_FT;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   const char* src = reinterpret_cast<const char*>(g - mis) + 16;
   char* dst = reinterpret_cast<char*>(words) + 16;
-  for (int k = 0; k < 9; ++k) {
+  for (int k = 0; k < F_PIECES; ++k) {
     const int c0 = k * PC;
     int n = NI - c0;
     if (n > PC) n = PC;
@@ -668,7 +668,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       const float* g0 = P.logits + (size_t)row * (size_t)P.ld;
       const int NI0 = ((((int)(((uintptr_t)g0 & 15u) >> 2)) + V + 3) >> 2) - 2;
       for (int k = 0; k < F_PIECES; ++k)
-        if (NI0 - k * 3 * FT > 0) { f_mbar_wait(&sc->bar[k], (parity >> k) & 1u); parity ^= (1u << k); }
+        if (NI0 - k * F_SUB * 3 * FT > 0) { f_mbar_wait(&sc->bar[k], (parity >> k) & 1u); parity ^= (1u << k); }
     }
 #endif
   };
@@ -695,7 +695,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     const int mis = (int)(((uintptr_t)g & 15u) >> 2);
     const int W4 = (mis + V + 3) >> 2;                     // float4 chunks of the padded row
     const int NI = W4 - 2;                                 // interior chunks: wholly inside the row
-    const int PC = 3 * FT;                                 // chunks per piece: every thread does 3 of each piece
+    const int PC = F_SUB * 3 * FT;                         // chunks per piece: every thread does F_SUB x 3 of each piece
     (void)PC;
 #if NSF_STREAM
     const float4* g4 = reinterpret_cast<const float4*>(g - mis);   // 16-byte aligned view of the row
@@ -820,14 +820,17 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       int c1 = c0 + PC;
       if (c1 > 1 + NI) c1 = 1 + NI;
       if (c0 < c1) { f_mbar_wait(&sc->bar[k], (parity >> k) & 1u); parity ^= (1u << k); }
-      // a piece is 3 float4 per thread: load all three, then run the three dependent chains interleaved
-      const int ca = c0 + tid, cb = ca + FT, cc = cb + FT;
-      if (cc < c1) {
-        const float4 va = w4[ca], vb = w4[cb], vc = w4[cc];
-        online12(va, vb, vc, ca, cb, cc);
-      } else {
-        if (ca < c1) online4(w4[ca], 4 * ca - mis);
-        if (cb < c1) online4(w4[cb], 4 * cb - mis);
+      // blocks of 3 float4 per thread: load all three, then run the three dependent chains interleaved
+#pragma unroll 1
+      for (int sb = 0; sb < F_SUB; ++sb) {
+        const int ca = c0 + sb * 3 * FT + tid, cb = ca + FT, cc = cb + FT;
+        if (cc < c1) {
+          const float4 va = w4[ca], vb = w4[cb], vc = w4[cc];
+          online12(va, vb, vc, ca, cb, cc);
+        } else {
+          if (ca < c1) online4(w4[ca], 4 * ca - mis);
+          if (cb < c1) online4(w4[cb], 4 * cb - mis);
+        }
       }
     }
 #endif

@@ -278,7 +278,7 @@ def test_rank_form_fast_path_matches_exact_kernel(V, precision, topk, temp, scal
     for name in ("tokens", "lo", "hi", "cursor", "ntok"):
         assert torch.equal(getattr(a, name), getattr(b, name)), name
     assert int((a.status & 3).sum().item()) == 0
-    if (topk, quant, scale) == (300, 0.0, 3.0):
+    if (topk, quant, scale) == (300, 0.0, 3.0) and a.variant == 0:   # (the streaming variant has no rank-form path)
         # config 2's settings on ordinary rows: the rank-form path of the throughput kernel codes every row itself
         assert int(((a.status & 4) != 0).sum().item()) == 0
     toks = a.token_lists()
