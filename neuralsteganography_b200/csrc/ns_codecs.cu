@@ -42,7 +42,7 @@ __device__ __forceinline__ CodecShared carve(unsigned char* smem_raw) {
 // bulk row staging: the copy engine writes the row into shared memory in C_PIECES pieces while the
 // CTA reduces its extent piece by piece (one pass instead of load + store + extent pass)
 // ------------------------------------------------------------------------------------------
-constexpr int C_PIECES = 6;
+constexpr int C_PIECES = 2;
 __device__ __forceinline__ uint32_t c_saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void c_mbar_init(u64* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(c_saddr(bar)), "r"(count));
