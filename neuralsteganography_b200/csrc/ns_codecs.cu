@@ -601,12 +601,12 @@ __global__ void __launch_bounds__(NT, 1) bins_kernel(ns_codec_params P) {
 // Throughput form of the bins encoder: one persistent CTA per SM = 16 consumer warps + 1 producer warp.
 // The word->bin table is staged once per CTA in shared memory as 16-bit entries; the logits rows stream
 // through a ring of bulk-copy slots (full/empty mbarriers, no CTA-wide barrier per slot), so the copy engine
-// keeps BINS_RING x 12 KB in flight per SM across row boundaries, independent of warp scheduling.
+// keeps BINS_RING x 56 KB in flight per SM across row boundaries, independent of warp scheduling.
 // HBM-bound: 4*V bytes per token, ~6 instructions per element.
 constexpr int BT = 512;                   // consumer threads per CTA
-constexpr int BINS_RING = 4;              // slots in flight (4 x 24 KB)
-constexpr int BINS_CPT = 3;               // float4 chunks per consumer thread and slot
-constexpr int BINS_PC = BINS_CPT * BT;    // float4 chunks per slot (24 KB)
+constexpr int BINS_RING = 2;              // slots in flight (2 x 56 KB)
+constexpr int BINS_CPT = 7;               // float4 chunks per consumer thread and slot
+constexpr int BINS_PC = BINS_CPT * BT;    // float4 chunks per slot (56 KB)
 struct BinsRow { int row, slot, bin, cursor, mlen; };
 __device__ __forceinline__ void c_mbar_arrive(u64* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(c_saddr(bar)) : "memory");
