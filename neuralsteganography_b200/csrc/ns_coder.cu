@@ -473,6 +473,10 @@ namespace nsf_stream {
 #undef NSF_FT
 #undef NSF_MIN_CTAS
 }  // namespace nsf_stream
+// two rows in flight per SM: one in shared memory, one in tensor memory (threshold form of the cutoff)
+namespace nsd {
+#include "ns_duo.cuh"
+}  // namespace nsd
 
 // ------------------------------------------------------------------------------------
 // host side
@@ -557,6 +561,20 @@ int launch_fast(const ns_ac_params* p, cudaStream_t st) {
   return check_launch();
 }
 
+// two-row kernel: persistent, one 512-thread CTA per SM = two 8-warp groups with a row each
+template <bool UNIT, int MODE>
+int launch_duo(const ns_ac_params* p, cudaStream_t st) {
+  const int smem = nsd::D_FIXED + (p->V + 8) * 4;
+  static bool configured = false;
+  int rc = configure(nsd::ac_duo_kernel<UNIT, MODE>, &configured);
+  if (rc != NS_OK) return rc;
+  if (p->B == 0) return NS_OK;
+  const int sms = num_sms();
+  const int grid = (p->B + 1) / 2 < sms ? (p->B + 1) / 2 : sms;
+  nsd::ac_duo_kernel<UNIT, MODE><<<grid, 2 * nsd::GT, smem, st>>>(*p, p->slow_ws);
+  return check_launch();
+}
+
 // streaming variant: persistent, scratch_slots CTAs (a few per SM), shared memory only for tables and lists
 template <bool UNIT, int MODE>
 int launch_stream(const ns_ac_params* p, cudaStream_t st) {
@@ -588,7 +606,9 @@ int dispatch(const ns_ac_params* p, u64* dbg_q, u64* dbg_meta, void* stream) {
   // (top-k small enough to bind and to fit the rank-form lists: the instantiation that carries that path)
   constexpr int M2 = MODE == MODE_DEBUG ? MODE_ENC : MODE;
   const bool rank = p->topk >= 2 && p->topk < p->V && p->topk <= nsf_smem::F_K_CAP;
+  const bool duo = !rank && p->variant != 2 && p->V >= nsd::D_MIN_VOCAB && p->V <= nsd::D_MAX_VOCAB;
   if (rank) rc = (p->temp == 1.0) ? launch_fast<true, M2, true>(p, st) : launch_fast<false, M2, true>(p, st);
+  else if (duo) rc = (p->temp == 1.0) ? launch_duo<true, M2>(p, st) : launch_duo<false, M2>(p, st);
   else rc = (p->temp == 1.0) ? launch_fast<true, M2, false>(p, st) : launch_fast<false, M2, false>(p, st);
   if (rc != NS_OK) return rc;
   return launch_exact<MODE, uint32_t>(p, dbg_q, dbg_meta, p->slow_ws, st);

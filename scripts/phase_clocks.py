@@ -25,6 +25,15 @@ for mode in ("enc", "dec"):
     for t in range(3): step(pool[t % P])
     torch.cuda.synchronize()
     pr = st.prof.cpu().numpy().astype(np.float64)
+    if os.environ.get("DUO", "1") == "1" and TOPK >= V:
+        for gi, gname in enumerate(("group 0 (row in shared memory)", "group 1 (row in tensor memory)")):
+            q = pr[16 * gi: 16 * gi + 16]
+            if q[15] == 0:
+                continue
+            print(mode, gname, "rows", int(q[15]), "cycles/row total %.0f" % (q[:11].sum() / q[15]))
+            for k, nm in enumerate(names[:11]):
+                print("   %-18s %8.0f cyc/row %5.1f%%" % (nm, q[k] / q[15], 100 * q[k] / q[:11].sum()))
+        continue
     rows = pr[15]
     print(mode, "rows", int(rows), "cycles/row total %.0f" % (pr[:11].sum() / rows))
     if pr[16:25].any():
