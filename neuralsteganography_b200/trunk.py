@@ -75,6 +75,7 @@ class StaticGPT2:
         self.v = torch.zeros_like(self.k)
         self.length = torch.zeros((), dtype=torch.long, device=self.device)   # tokens in the cache (same for all streams)
         self._arange_t = torch.arange(self.T, device=self.device)
+        self._host_len = 0                                  # host copy of `length` while only eager calls touched it
         self.window = 1022                                  # utils.py:19-30 (hard-coded in the reference)
         self.ring = self.window + 1 if self.T >= self.window + 1 else 0   # ring slots; 0 = plain buffer
 
@@ -107,8 +108,49 @@ class StaticGPT2:
             h = F.layer_norm(x, (self.n_embd,), w["ln2w"], w["ln2b"], self.eps)
             x = x + (F.gelu(h @ w["fcw"] + w["fcb"], approximate="tanh") @ w["ow"] + w["ob"])
         self.length.fill_(L)
+        self._host_len = L
         x = F.layer_norm(x[:, -1], (self.n_embd,), self.lnfw, self.lnfb, self.eps)
         return (x @ self.lm_head.t()).float().contiguous()
+
+    # ------------------------------------------------------------------ a tile of known tokens (teacher forcing, eager)
+    @torch.no_grad()
+    def extend(self, tokens: torch.Tensor) -> torch.Tensor:
+        """Append the known tokens ``[B, W]`` at positions ``length .. length+W-1`` in one pass (causal inside the
+        tile, full attention to the cache); returns fp32 logits ``[B, W, V]`` -- entry ``j`` is the distribution of the
+        token that follows ``tokens[:, j]``.  Serves covers that stay inside the KV buffer / the 1022-token window."""
+        with _matmul_tf32(self.tf32):
+            return self._extend(tokens)
+
+    def _extend(self, tokens: torch.Tensor) -> torch.Tensor:
+        B, W = tokens.shape
+        L = self._host_len if self._host_len is not None else int(self.length.item())
+        limit = self.ring if self.ring else self.T
+        if B != self.B or L + W > limit:
+            raise ValueError("extend: %d cached + %d new tokens exceed the %d usable KV slots" % (L, W, limit))
+        pos = torch.arange(L, L + W, device=self.device).remainder(self.n_positions)     # arithmetic.py:44-48
+        x = self.wte[tokens] + self.wpe[pos][None]
+        keys = torch.arange(L + W, device=self.device)
+        allowed = (keys[None, :] <= (L + torch.arange(W, device=self.device))[:, None])[None, None]   # [1,1,W,L+W]
+        for i, w in enumerate(self.layers):
+            h = F.layer_norm(x, (self.n_embd,), w["ln1w"], w["ln1b"], self.eps)
+            qkv = h @ w["qkvw"] + w["qkvb"]
+            q, k, v = qkv.split(self.n_embd, dim=-1)
+            q = q.view(B, W, self.n_head, self.hd).transpose(1, 2)
+            k = k.view(B, W, self.n_head, self.hd).transpose(1, 2)
+            v = v.view(B, W, self.n_head, self.hd).transpose(1, 2)
+            self.k[i][:, :, L:L + W] = k
+            self.v[i][:, :, L:L + W] = v
+            kk, vv = self.k[i][:, :, :L + W], self.v[i][:, :, :L + W]
+            att = (q @ kk.transpose(-1, -2)) / math.sqrt(self.hd)
+            att = att.masked_fill(~allowed, torch.finfo(att.dtype).min).softmax(-1)
+            a = (att @ vv).transpose(1, 2).reshape(B, W, self.n_embd)
+            x = x + (a @ w["pw"] + w["pb"])
+            h = F.layer_norm(x, (self.n_embd,), w["ln2w"], w["ln2b"], self.eps)
+            x = x + (F.gelu(h @ w["fcw"] + w["fcb"], approximate="tanh") @ w["ow"] + w["ob"])
+        self.length.fill_(L + W)
+        self._host_len = L + W
+        x = F.layer_norm(x, (self.n_embd,), self.lnfw, self.lnfb, self.eps)
+        return (x @ self.lm_head.t()).float()
 
     # ------------------------------------------------------------------ one token (fixed shapes, graph-capturable)
     @torch.no_grad()
@@ -159,8 +201,10 @@ class StaticGPT2:
             h = F.layer_norm(x, (self.n_embd,), w["ln2w"], w["ln2b"], self.eps)
             x = x + (F.gelu(h @ w["fcw"] + w["fcb"], approximate="tanh") @ w["ow"] + w["ob"])
         self.length.add_(1)
+        self._host_len = None                               # replayed under CUDA graphs: the host no longer knows the length
         x = F.layer_norm(x, (self.n_embd,), self.lnfw, self.lnfb, self.eps)
         return (x @ self.lm_head.t()).float().contiguous()
 
     def reset(self) -> None:
         self.length.zero_()
+        self._host_len = 0

@@ -96,3 +96,23 @@ def test_kv_bucket_prefix_gives_the_same_logits():
         assert torch.allclose(a.step(tok), b.step(tok, b.kv_bucket(L + s + 1)), atol=1e-6), s
     ring = StaticGPT2(model, B, max_len=1024, device="cpu")
     assert ring.kv_bucket(1023) == 1024 and ring.kv_bucket(1024) == 1024 and ring.kv_bucket(5000) == 1024
+
+
+def test_extend_tiles_match_token_steps():
+    """Teacher-forced tiles (``extend``) give the logits of the one-token steps (config 4's batched decode)."""
+    model = _tiny()
+    B, L, n = 2, 5, 11
+    g = torch.Generator().manual_seed(9)
+    ctx = torch.randint(0, 96, (B, L), generator=g)
+    toks = torch.randint(0, 96, (B, n), generator=g)
+    a = StaticGPT2(model, B, max_len=64, device="cpu")
+    b = StaticGPT2(model, B, max_len=64, device="cpu")
+    a.prefill(ctx); b.prefill(ctx)
+    steps = torch.stack([a.step(toks[:, j]) for j in range(n)], dim=1)          # [B, n, V]
+    tiles = torch.cat([b.extend(toks[:, :4]), b.extend(toks[:, 4:5]), b.extend(toks[:, 5:])], dim=1)
+    assert tiles.shape == steps.shape
+    assert torch.allclose(tiles, steps, atol=1e-5, rtol=1e-5)
+    assert int(b.length) == L + n
+    import pytest
+    with pytest.raises(ValueError):
+        b.extend(torch.zeros(B, 64, dtype=torch.long))
