@@ -111,12 +111,13 @@ typedef struct ns_ac_params {
      log p(selected token), KL(q_hat || p) in bits, entropy of the tempered distribution in bits.
      Requesting them routes the step through the exact kernel. */
   double* stats;
-  /* Streaming variant of the throughput kernel (several CTAs per SM, no row in shared memory, no
-     vocabulary limit): per-CTA scratch rows in global memory, scratch_slots rows of scratch_stride
-     bytes (16-byte multiple, >= 4*(V+8)).  Used when variant == 1 and scratch is given. */
+  /* Reserved (a former streaming variant kept its scratch rows here); must be NULL / 0. */
   void* scratch;
   int64_t scratch_stride;
   int32_t scratch_slots;
+  /* Kernel choice for the throughput path: 0 = default (threshold form of the cutoff: two rows in flight per SM, one
+     in shared memory and one in tensor memory, when V fits ns_ac_duo_max_vocab(); rank form and everything else: one
+     row per SM in shared memory), 2 = always the single-row kernel.  Results are identical. */
   int32_t variant;
 } ns_ac_params;
 
@@ -124,8 +125,10 @@ int ns_version(void);
 const char* ns_last_error_string(void);
 /* sizeof(ns_ac_params) as compiled, so a binding can verify its struct mirror */
 int ns_sizeof_ac_params(void);
-/* largest V the arithmetic-coder kernels accept on this build */
+/* largest V the arithmetic-coder kernels accept on this build (the row lives in shared memory) */
 int ns_ac_max_vocab(void);
+/* largest V the two-row kernel accepts (it needs a second scratch set beside the shared-memory row) */
+int ns_ac_duo_max_vocab(void);
 
 /* one encode step for B streams (code_base/arithmetic.py:114-210 loop body) */
 int ns_ac_encode_step(const ns_ac_params* p, void* cuda_stream);

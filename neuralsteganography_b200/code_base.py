@@ -60,7 +60,10 @@ def decode_arithmetic(model, enc, text, context: Sequence[int], device: str = "c
     from .reveal import SequentialDecoder
     inp = enc.encode(text) if isinstance(text, str) else [int(t) for t in text]
     trunk = StaticGPT2(model, 1, max_len=max(max_len, min(1024, len(context) + 2 * len(inp) + 80)), device=device)
-    dec = SequentialDecoder(trunk, enc, precision=precision, temp=temp, topk=topk, device=device)
+    # encode_arithmetic collects the reference's statistics, which only the exact kernel computes: decode with the same
+    # kernel, so that both directions share one summation tree (the throughput kernel agrees with it to ~1e-7 per row,
+    # not by construction)
+    dec = SequentialDecoder(trunk, enc, precision=precision, temp=temp, topk=topk, device=device, force_exact=True)
     bits, _tokens, _used = dec.run(list(context), inp)
     return bits
 

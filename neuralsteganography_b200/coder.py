@@ -62,11 +62,11 @@ class ArithmeticStreams:
                  topk: int = 50000, finish_sent: bool = False, device="cuda",
                  mask_ids: Optional[Sequence[int]] = None, token_cap: int = 1024,
                  sent_end: Optional[torch.Tensor] = None, trace: bool = False, force_exact: bool = False,
-                 variant: Optional[int] = None, scratch_slots: Optional[int] = None):
+                 variant: Optional[int] = None):
         self.lib = N.load()
         if not torch.cuda.is_available():
             raise N.NativeLibraryError("no CUDA device: the coder has no CPU fallback")
-        if vocab > self.lib.ns_ac_max_vocab() and (variant or 0) != 1:
+        if vocab > self.lib.ns_ac_max_vocab():
             raise N.NativeLibraryError("vocab %d exceeds kernel capacity %d" % (vocab, self.lib.ns_ac_max_vocab()))
         self.B, self.V = int(batch), int(vocab)
         self.precision, self.temp, self.topk = int(precision), float(temp), int(topk)
@@ -89,17 +89,10 @@ class ArithmeticStreams:
         self.sent_end = sent_end
         self.force_exact = bool(force_exact)
         self.slow_ws = torch.zeros(self.B + 2, dtype=torch.int32, device=d)
-        # kernel variant: 0 = row resident in shared memory (one CTA per SM), 1 = streaming (several CTAs
-        # per SM, per-CTA scratch rows in L2-resident global memory, no vocabulary limit)
+        # kernel choice of the throughput path: 0 = default (two rows in flight per SM for the threshold form of the
+        # cutoff), 2 = always the single-row kernel (NS_AC_VARIANT overrides; results are identical)
         import os as _os
         self.variant = int(_os.environ.get("NS_AC_VARIANT", "0")) if variant is None else int(variant)
-        self.scratch = None
-        self.scratch_stride = ((self.V + 8) * 4 + 127) // 128 * 128
-        self.scratch_slots = 0
-        if self.variant == 1:
-            sms = torch.cuda.get_device_properties(d).multi_processor_count
-            self.scratch_slots = int(scratch_slots or _os.environ.get("NS_AC_SLOTS", 2 * sms))
-            self.scratch = torch.empty(self.scratch_slots * self.scratch_stride, dtype=torch.uint8, device=d)
         self.msg = None
         self.msg_len = None
         self.ntok_total = None
@@ -188,8 +181,7 @@ class ArithmeticStreams:
         p.force_exact = int(self.force_exact)
         p.prof = N.ptr(getattr(self, "prof", None))
         p.stats = N.ptr(getattr(self, "stats", None))
-        p.scratch = N.ptr(self.scratch); p.scratch_stride = self.scratch_stride
-        p.scratch_slots = self.scratch_slots; p.variant = self.variant
+        p.scratch = None; p.scratch_stride = 0; p.scratch_slots = 0; p.variant = self.variant
         return p
 
     def encode_step(self, logits: torch.Tensor) -> None:

@@ -454,25 +454,14 @@ __global__ void __launch_bounds__(NT, 1) ac_step_kernel(ns_ac_params P, u64* dbg
   }
 }
 
-// the throughput kernel, compiled in its two variants (see the head of ns_fast.cuh)
+// the single-row throughput kernel (carries the rank form of the cutoff; see the head of ns_fast.cuh)
 namespace nsf_smem {
-#define NSF_STREAM 0
 #define NSF_FT 512
 #define NSF_MIN_CTAS 1
 #include "ns_fast.cuh"
-#undef NSF_STREAM
 #undef NSF_FT
 #undef NSF_MIN_CTAS
 }  // namespace nsf_smem
-namespace nsf_stream {
-#define NSF_STREAM 1
-#define NSF_FT 256
-#define NSF_MIN_CTAS 2
-#include "ns_fast.cuh"
-#undef NSF_STREAM
-#undef NSF_FT
-#undef NSF_MIN_CTAS
-}  // namespace nsf_stream
 // two rows in flight per SM: one in shared memory, one in tensor memory (threshold form of the cutoff)
 namespace nsd {
 #include "ns_duo.cuh"
@@ -506,25 +495,19 @@ int validate(const ns_ac_params* p, int mode) {
   return NS_OK;
 }
 
-int g_num_sms = 0;
-
+// SM count and the shared-memory opt-in are properties of the CURRENT device: asked per call (both are cheap host-side
+// lookups), so a process that drives several GPUs or several host threads gets the right answer on each.
 int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      g_num_sms = n;
-    else
-      g_num_sms = 148;
-  }
-  return g_num_sms;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+    return n;
+  return 148;
 }
 
 template <typename K>
-int configure(K kernel, bool* done) {
-  if (*done) return NS_OK;
+int configure(K kernel, bool*) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
   if (e != cudaSuccess) { set_err((int)e, cudaGetErrorString(e)); return e == cudaErrorInvalidDeviceFunction ? NS_E_NODEVICE : (int)e; }
-  *done = true;
   return NS_OK;
 }
 
@@ -575,18 +558,6 @@ int launch_duo(const ns_ac_params* p, cudaStream_t st) {
   return check_launch();
 }
 
-// streaming variant: persistent, scratch_slots CTAs (a few per SM), shared memory only for tables and lists
-template <bool UNIT, int MODE>
-int launch_stream(const ns_ac_params* p, cudaStream_t st) {
-  static bool configured = false;
-  int rc = configure(nsf_stream::ac_fast_kernel<UNIT, MODE>, &configured);
-  if (rc != NS_OK) return rc;
-  if (p->B == 0) return NS_OK;
-  const int grid = p->B < p->scratch_slots ? p->B : p->scratch_slots;
-  nsf_stream::ac_fast_kernel<UNIT, MODE><<<grid, nsf_stream::FT, FIXED_BYTES, st>>>(*p, p->slow_ws);
-  return check_launch();
-}
-
 template <int MODE>
 int dispatch(const ns_ac_params* p, u64* dbg_q, u64* dbg_meta, void* stream) {
   int rc = validate(p, MODE);
@@ -595,13 +566,6 @@ int dispatch(const ns_ac_params* p, u64* dbg_q, u64* dbg_meta, void* stream) {
   if (p->precision > 31) return launch_exact<MODE, u64>(p, dbg_q, dbg_meta, nullptr, st);
   if (MODE == MODE_DEBUG || p->slow_ws == nullptr || p->force_exact || p->V < nsf_smem::F_MIN_VOCAB || p->stats != nullptr)
     return launch_exact<MODE, uint32_t>(p, dbg_q, dbg_meta, nullptr, st);
-  if (p->variant == 1 && p->scratch != nullptr && p->scratch_slots > 0 && p->scratch_stride >= (int64_t)(p->V + 8) * 4 &&
-      (p->scratch_stride & 15) == 0) {
-    rc = (p->temp == 1.0) ? launch_stream<true, MODE == MODE_DEBUG ? MODE_ENC : MODE>(p, st)
-                          : launch_stream<false, MODE == MODE_DEBUG ? MODE_ENC : MODE>(p, st);
-    if (rc != NS_OK) return rc;
-    return launch_exact<MODE, uint32_t>(p, dbg_q, dbg_meta, p->slow_ws, st);
-  }
   // throughput path: fast kernel, then the exact kernel on whatever it handed over
   // (top-k small enough to bind and to fit the rank-form lists: the instantiation that carries that path)
   constexpr int M2 = MODE == MODE_DEBUG ? MODE_ENC : MODE;
@@ -621,6 +585,7 @@ extern "C" {
 int ns_version(void) { return NS_ABI_VERSION; }
 const char* ns_last_error_string(void) { return g_err; }
 int ns_ac_max_vocab(void) { return MAX_VOCAB; }
+int ns_ac_duo_max_vocab(void) { return nsd::D_MAX_VOCAB; }
 int ns_sizeof_ac_params(void) { return (int)sizeof(ns_ac_params); }
 
 int ns_ac_encode_step(const ns_ac_params* p, void* cuda_stream) { return dispatch<MODE_ENC>(p, nullptr, nullptr, cuda_stream); }

@@ -22,16 +22,7 @@
 // Anything unusual (list overflows, estimate outside its guard band, rank form beyond the lists) queues
 // the row in slow_ws; the exact multi-pass kernel then redoes it with the same integers.
 
-// This header is compiled twice (ns_coder.cu), each time inside its own namespace:
-//   NSF_STREAM 0  one CTA per SM, 512 threads, the row resident in shared memory (bulk copy);
-//   NSF_STREAM 1  several smaller CTAs per SM, nothing of the row in shared memory: the logits are
-//                 streamed from HBM (estimate) and again from L2 (exp pass), the packed e words live in a
-//                 per-CTA global scratch row that stays in L2.  Rows of different CTAs are in different
-//                 phases, so the phases that stall on one pipe overlap with those that stall on another,
-//                 and the vocabulary is no longer bounded by shared memory.
-#ifndef NSF_STREAM
-#define NSF_STREAM 0
-#endif
+// One CTA per SM, 512 threads, the row resident in shared memory (bulk copy).
 #ifndef NSF_FT
 #define NSF_FT 512
 #endif
@@ -114,12 +105,10 @@ __device__ __forceinline__ void f_mbar_wait(u64* bar, uint32_t parity) {
       "}\n" :: "r"(f_smem_addr(bar)), "r"(parity) : "memory");
 }
 
-#if !NSF_STREAM
 // Bulk copy of row `row` into the shared-memory row (interior float4 chunks 1 .. W4-2, F_PIECES pieces, one
 // mbarrier each).  One thread.  Every generic-proxy access of the buffer's previous content must be behind a
 // CTA barrier; the proxy fence orders them before the async-proxy writes.
 __device__ __forceinline__ void f_issue_row(const ns_ac_params& P, int row, u64* bar, float* words, int* issued_row);
-#endif
 
 // The exp pass leaves, in place of each kept logit, a 32-bit truncation of its fp64 e: the double's
 // bits 59..28 (low 8 exponent bits + 24 mantissa bits; for 2^-255 < e <= 1 the four bits above are the
@@ -220,7 +209,6 @@ __device__ __forceinline__ void f_sum_ddu(double& a, double& b, u64& c, u64* scr
   a = ra; b = rb; c = rc;
 }
 
-#if !NSF_STREAM
 __device__ __forceinline__ void f_issue_row(const ns_ac_params& P, int row, u64* bar, float* words, int* issued_row) {
   const float* g = P.logits + (size_t)row * (size_t)P.ld;
   const int mis = (int)(((uintptr_t)g & 15u) >> 2);
@@ -240,11 +228,9 @@ __device__ __forceinline__ void f_issue_row(const ns_ac_params& P, int row, u64*
   }
   *issued_row = row;
 }
-#endif
 
 struct FastSmem {
   double* tab; uint32_t* hist; BandEntry* band; int* ulist; CandEntry* clist; FScal* sc; float* words;
-  // NSF_STREAM: `words` is this CTA's global scratch row (16-byte aligned), else the shared-memory row
 };
 
 __device__ __forceinline__ RowMeta f_load_meta(const ns_ac_params& P, int row, int mode) {
@@ -307,7 +293,6 @@ struct PhaseClock {
 };
 
 
-#if !NSF_STREAM
 // ------------------------------------------------------------------------------------------------
 // Rank form of the cutoff (code_base/arithmetic.py:75 with top-k binding: k = topk because more than
 // topk tokens have p >= 1/range).  Only the topk largest logits matter, so no pass over the row touches
@@ -613,7 +598,6 @@ __device__ __noinline__ int fast_rank_row(const ns_ac_params& P, int32_t* slow_w
   }
   return 1;
 }
-#endif
 
 template <bool UNIT_TEMP, int MODE, bool RANK>
 __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws, const int row, const RowMeta meta,
@@ -623,29 +607,13 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
   float4* w4 = reinterpret_cast<float4*>(words);
   // packed-word storage: shared memory, or (stream variant) L2-resident global scratch
   auto word_ld4 = [&](int c) -> float4 {
-#if NSF_STREAM
-    float4 v;
-    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(w4 + c));
-    return v;
-#else
     return w4[c];
-#endif
   };
   auto word_st4 = [&](int c, const float4 v) {
-#if NSF_STREAM
-    asm volatile("st.global.cg.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(w4 + c), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-#else
     w4[c] = v;
-#endif
   };
   auto word_ld1 = [&](int i) -> float {
-#if NSF_STREAM
-    float v;
-    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(words + i));
-    return v;
-#else
     return words[i];
-#endif
   };
   const int tid = threadIdx.x;
   const int V = P.V;
@@ -655,22 +623,18 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
   // Called by every thread right after a CTA barrier that follows the row's last access to the shared-memory
   // row: thread 0 starts the next row's bulk copy, whose latency then overlaps the rest of this row.
   auto next_row_copy = [&]() {
-#if !NSF_STREAM
     const int nrow = row + (int)gridDim.x;
     if (tid == 0 && nrow < P.B) f_issue_row(P, nrow, sc->bar, words, &sc->issued_row);
-#endif
   };
   int phase = meta.phase;
   // a row that is skipped still has to consume its bulk copy if the previous row already started it
   auto drain = [&]() {
-#if !NSF_STREAM
     if (sc->issued_row == row) {
       const float* g0 = P.logits + (size_t)row * (size_t)P.ld;
       const int NI0 = ((((int)(((uintptr_t)g0 & 15u) >> 2)) + V + 3) >> 2) - 2;
       for (int k = 0; k < F_PIECES; ++k)
         if (NI0 - k * F_SUB * 3 * FT > 0) { f_mbar_wait(&sc->bar[k], (parity >> k) & 1u); parity ^= (1u << k); }
     }
-#endif
   };
   if (phase == NS_PHASE_DONE) { drain(); return; }
   if (MODE != MODE_ENC) phase = NS_PHASE_CODING;
@@ -697,37 +661,6 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     const int NI = W4 - 2;                                 // interior chunks: wholly inside the row
     const int PC = F_SUB * 3 * FT;                         // chunks per piece: every thread does F_SUB x 3 of each piece
     (void)PC;
-#if NSF_STREAM
-    const float4* g4 = reinterpret_cast<const float4*>(g - mis);   // 16-byte aligned view of the row
-    if (tid == 0) { sc->band_n = 0; sc->u_n = 0; sc->c_n = 0; sc->bail = 0; sc->band_cut_int = 0; sc->remax = 0; sc->band_kept_n = 0; }
-    // raw chunk c of the logits row: aligned 128-bit loads, the two edge chunks element-wise with -inf padding
-    auto raw4_l = [&](int c) -> float4 {
-      float4 v;
-      if (c > 0 && c < W4 - 1) {
-        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(g4 + c));
-      } else {
-        const int b = 4 * c - mis;
-        v.x = (b >= 0 && b < V) ? g[b] : -INFINITY;
-        v.y = (b + 1 >= 0 && b + 1 < V) ? g[b + 1] : -INFINITY;
-        v.z = (b + 2 >= 0 && b + 2 < V) ? g[b + 2] : -INFINITY;
-        v.w = (b + 3 >= 0 && b + 3 < V) ? g[b + 3] : -INFINITY;
-      }
-      return v;
-    };
-    // the same with the forbidden tokens (arithmetic.py:124-125) at -inf: the logits tensor is read-only
-    const int mk0 = (P.mask_id[0] >= 0 && P.mask_id[0] < V) ? P.mask_id[0] + mis : -8;
-    const int mk1 = (P.mask_id[1] >= 0 && P.mask_id[1] < V) ? P.mask_id[1] + mis : -8;
-    auto raw4_p = [&](int c) -> float4 {
-      float4 v = raw4_l(c);
-      if (c == (mk0 >> 2) || c == (mk1 >> 2)) {
-        float* f = reinterpret_cast<float*>(&v);
-        if (c == (mk0 >> 2)) f[mk0 & 3] = -INFINITY;
-        if (c == (mk1 >> 2)) f[mk1 & 3] = -INFINITY;
-      }
-      return v;
-    };
-#else
     if (tid == 0) {
       // (unless the previous row already started this copy once it was done with the buffer)
       if (sc->issued_row != row) f_issue_row(P, row, sc->bar, words, &sc->issued_row);
@@ -741,17 +674,9 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     }
     auto raw4_l = [&](int c) -> float4 { return w4[c]; };
     auto raw4_p = [&](int c) -> float4 { return w4[c]; };    // masks are written into the shared row after L
-#endif
     for (int i = tid; i < F_NB / 4; i += FT) reinterpret_cast<uint4*>(hist)[i] = make_uint4(0, 0, 0, 0);
     {   // prefetch this CTA's next row into L2 while this one is processed
       const int nrow = row + gridDim.x;
-#if NSF_STREAM
-      if (nrow < P.B) {
-        const char* np = reinterpret_cast<const char*>(P.logits + (size_t)nrow * (size_t)P.ld);
-        const int nbytes = V * 4;
-        for (int off = tid * 128; off < nbytes; off += FT * 128) f_prefetch_l2(np + off);
-      }
-#else
       // one bulk prefetch per warp leader: the copy engine walks the lines.  Per-lane prefetch instructions
       // (32 lines each) occupy the load/store pipe for ~1.5k cycles and hold back the estimate's shared loads.
       if (nrow < P.B && (tid & 31) == 0) {
@@ -764,7 +689,6 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
         if (n > per) n = per;
         if (n > 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a0 + o), "r"(n) : "memory");
       }
-#endif
     }
     pc.mark(0);                                            // row prologue: copy issue, edges, prefetch
     // fp32 online softmax over the pieces as they land: (tm, ts) per thread, lowest id of the max
@@ -802,19 +726,6 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       const float sc3 = (f_ex2(fmaf(vc.x, c2, ntc)) + f_ex2(fmaf(vc.y, c2, ntc))) + (f_ex2(fmaf(vc.z, c2, ntc)) + f_ex2(fmaf(vc.w, c2, ntc)));
       ts += (sa + sb) + sc3;
     };
-#if NSF_STREAM
-    // interior chunks 1 .. W4-2 straight from global memory, three 128-bit loads in flight per thread
-    for (int ca = 1 + tid; ca < 1 + NI; ca += 6 * FT) {
-      const int cb = ca + FT, cc = cb + FT, cd = cc + FT, ce = cd + FT, cf = ce + FT;
-      if (cf < 1 + NI) {
-        const float4 va = raw4_l(ca), vb = raw4_l(cb), vc = raw4_l(cc), vd = raw4_l(cd), ve = raw4_l(ce), vf = raw4_l(cf);
-        online12(va, vb, vc, ca, cb, cc);
-        online12(vd, ve, vf, cd, ce, cf);
-      } else {
-        for (int c = ca; c < 1 + NI; c += FT) online4(raw4_l(c), 4 * c - mis);
-      }
-    }
-#else
     for (int k = 0; k < F_PIECES; ++k) {
       const int c0 = 1 + k * PC;
       int c1 = c0 + PC;
@@ -833,7 +744,6 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
         }
       }
     }
-#endif
     pc.mark(1);                                            // L: waits + estimate over the pieces
     __syncthreads();                                       // edge chunks written by threads 0..7
     {
@@ -871,7 +781,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const int id = P.mask_id[k];
-        if (id >= 0 && id < V) xmask[k] = NSF_STREAM ? g[id] : words[id + mis];
+        if (id >= 0 && id < V) xmask[k] = words[id + mis];
       }
       __syncthreads();
       const uint4 pr = red4[lane < FW ? lane : 0];
@@ -891,9 +801,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
         if (id >= 0 && id < V) {
           if (xmask[k] > -INFINITY) ssum -= f_ex2((xmask[k] - M) * c2);
           if (id == top_id) remax = true;
-#if !NSF_STREAM
           if (tid == k) words[id + mis] = -INFINITY;
-#endif
         }
       }
       __syncthreads();                                     // the -inf is visible to whoever sweeps the row next
@@ -932,13 +840,8 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
         for (int k = 0; k < 2; ++k) {
           const int id = P.mask_id[k];
           if (id >= 0 && id < V) {
-  #if NSF_STREAM
-            const float x = g[id];
-            if (x > -INFINITY) ssum -= f_ex2((x - M) * c2);
-  #else
             const float x = words[id + mis];
             if (x > -INFINITY) { ssum -= f_ex2((x - M) * c2); words[id + mis] = -INFINITY; }
-  #endif
             if (id == top_id) remax = 1;
           }
         }
@@ -1026,7 +929,6 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
       if (s < F_BAND_CAP) { band[s].id = id; band[s].kept = 0; band[s].e = e; }
     };
 
-#if !NSF_STREAM
     if (RANK && P.topk < V && P.topk >= 2 && P.topk <= F_K_CAP) {
       // top-k binds if more than topk tokens are above the cutoff even should the estimate be 2% off
       const float kappa_r = kappa_hi + 0.02f * (float)temp;
@@ -1036,23 +938,14 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
         return;
       }
     }
-#endif
     pc.mark(2);                                            // reductions, masks, row constants
     // ------------------------------------------------------------------ P1: the fp64 exp pass
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
     double accl0 = 0.0, accl1 = 0.0, accl2 = 0.0, accl3 = 0.0;
     int cnt_hi = 0;
     const bool need_count = P.topk < V;                      // otherwise only "at least 2 kept" matters
-#if NSF_STREAM
-    float4 v_next = (tid < W4) ? raw4_p(tid) : make_float4(0.f, 0.f, 0.f, 0.f);
-#endif
     for (int c = tid; c < W4; c += FT) {
-#if NSF_STREAM
-      const float4 v = v_next;                               // loaded one iteration ahead (L2 latency)
-      if (c + FT < W4) v_next = raw4_p(c + FT);
-#else
       const float4 v = raw4_p(c);
-#endif
       const int b = 4 * c - mis;
       const double e0 = ns_exp64_core(a_of(v.x), tab);
       const double e1 = ns_exp64_core(a_of(v.y), tab);
@@ -1546,21 +1439,15 @@ __global__ void __launch_bounds__(FT, NSF_MIN_CTAS) ac_fast_kernel(const __grid_
   sm.ulist = reinterpret_cast<int*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16);
   sm.clist = reinterpret_cast<CandEntry*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16 + F_U_CAP * 4);
   sm.sc = reinterpret_cast<FScal*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16 + F_U_CAP * 4 + 2 * F_C_CAP * 16);
-#if NSF_STREAM
-  sm.words = reinterpret_cast<float*>(reinterpret_cast<char*>(P.scratch) + (size_t)blockIdx.x * (size_t)P.scratch_stride);
-#else
   sm.words = reinterpret_cast<float*>(smem_raw + FIXED_BYTES);   // element id lives at words[id + mis]
-#endif
   const int tid = threadIdx.x;
   constexpr int HELPER = FT - 32;                          // lane that fetches the next row's scalars
   for (int i = tid; i < NS_EXP_N; i += FT) sm.tab[i] = c_exp_tab[i];
-#if !NSF_STREAM
   if (tid == 0) {
     for (int k = 0; k < F_PIECES; ++k) f_mbar_init(&sm.sc->bar[k], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     sm.sc->issued_row = -1;
   }
-#endif
   if (tid == HELPER && (int)blockIdx.x < P.B) sm.sc->meta[0] = f_load_meta(P, blockIdx.x, MODE);
   uint32_t parity = 0;                                     // bit k: phase parity of piece k's mbarrier
   PhaseClock pc;

@@ -105,13 +105,14 @@ def _lsb_bytes(bits: Sequence[int]) -> bytes:
 class SequentialDecoder:
     """One stream, one token at a time: trunk step + CUDA coder step, with the reference's BPE repair in between."""
 
-    def __init__(self, trunk, tokenizer, *, precision: int, temp: float, topk: int, device="cuda"):
+    def __init__(self, trunk, tokenizer, *, precision: int, temp: float, topk: int, device="cuda", force_exact: bool = False):
         # the trunk may be wider than one stream: the stream is then replicated over its rows so that the GEMM shapes
         # -- and with them the fp32 summation order of the logits -- are those of the batch that encoded the cover
         self.trunk, self.enc = trunk, tokenizer
         self.V = trunk.vocab
         self.precision, self.temp, self.topk = int(precision), float(temp), int(topk)
         self.device = torch.device(device)
+        self.force_exact = bool(force_exact)            # pair with an encoder that ran the exact kernel (statistics)
         self.repairs = 0
         self.unrepaired = 0
 
@@ -135,7 +136,7 @@ class SequentialDecoder:
         inp = prepass_628([int(t) for t in tokens])
         cap = len(inp) + len(inp) // 2 + 64
         st = ArithmeticStreams(1, self.V, precision=self.precision, temp=self.temp, topk=self.topk, token_cap=cap,
-                               device=self.device)
+                               device=self.device, force_exact=self.force_exact)
         st.set_tokens([inp])
         if not flush_last:
             st.ntok_total.fill_(cap + 1)                    # no token is "the last one" (arithmetic.py:356): spans end in band

@@ -129,21 +129,25 @@ class StaticGPT2:
             raise ValueError("extend: %d cached + %d new tokens exceed the %d usable KV slots" % (L, W, limit))
         pos = torch.arange(L, L + W, device=self.device).remainder(self.n_positions)     # arithmetic.py:44-48
         x = self.wte[tokens] + self.wpe[pos][None]
-        keys = torch.arange(L + W, device=self.device)
-        allowed = (keys[None, :] <= (L + torch.arange(W, device=self.device))[:, None])[None, None]   # [1,1,W,L+W]
+        # Linear layers run on all B*W rows at once.  Attention runs per position with exactly the shapes of `_step`
+        # (one query against the live KV bucket): cuBLAS' batched GEMM is not row-wise identical between 1 and W queries
+        # (tests/diag/gemm_invariance.py), and encoder and decoder must see bit-identical logits.
         for i, w in enumerate(self.layers):
             h = F.layer_norm(x, (self.n_embd,), w["ln1w"], w["ln1b"], self.eps)
             qkv = h @ w["qkvw"] + w["qkvb"]
             q, k, v = qkv.split(self.n_embd, dim=-1)
-            q = q.view(B, W, self.n_head, self.hd).transpose(1, 2)
-            k = k.view(B, W, self.n_head, self.hd).transpose(1, 2)
-            v = v.view(B, W, self.n_head, self.hd).transpose(1, 2)
-            self.k[i][:, :, L:L + W] = k
-            self.v[i][:, :, L:L + W] = v
-            kk, vv = self.k[i][:, :, :L + W], self.v[i][:, :, :L + W]
-            att = (q @ kk.transpose(-1, -2)) / math.sqrt(self.hd)
-            att = att.masked_fill(~allowed, torch.finfo(att.dtype).min).softmax(-1)
-            a = (att @ vv).transpose(1, 2).reshape(B, W, self.n_embd)
+            self.k[i][:, :, L:L + W] = k.view(B, W, self.n_head, self.hd).transpose(1, 2)
+            self.v[i][:, :, L:L + W] = v.view(B, W, self.n_head, self.hd).transpose(1, 2)
+            outs = []
+            for j in range(W):
+                Tk = self.kv_bucket(L + j + 1)
+                qj = q[:, j].reshape(B, self.n_head, 1, self.hd)
+                kk, vv = self.k[i][:, :, :Tk], self.v[i][:, :, :Tk]
+                live = (self._arange_t[:Tk] <= L + j)[None, None, None, :]
+                att = (qj @ kk.transpose(-1, -2)) / math.sqrt(self.hd)
+                att = att.masked_fill(~live, torch.finfo(att.dtype).min).softmax(-1)
+                outs.append((att @ vv).reshape(B, self.n_embd))
+            a = torch.stack(outs, dim=1)
             x = x + (a @ w["pw"] + w["pb"])
             h = F.layer_norm(x, (self.n_embd,), w["ln2w"], w["ln2b"], self.eps)
             x = x + (F.gelu(h @ w["fcw"] + w["fcb"], approximate="tanh") @ w["ow"] + w["ob"])
