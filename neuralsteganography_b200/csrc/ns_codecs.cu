@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "ns_block.cuh"
 
@@ -799,6 +800,20 @@ int validate_codec(const ns_codec_params* p, int kind) {
   return NS_OK;
 }
 
+#include "ns_codecs_stream.cuh"
+
+// row-streaming kernels: one small CTA per row, several rows per SM
+template <typename K>
+int launch_stream_codec(K kernel, const ns_codec_params* p, void* stream) {
+  if (p->B == 0) return NS_OK;
+  kernel<<<p->B, CT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cerr((int)e, cudaGetErrorString(e));
+  return NS_OK;
+}
+// rows they serve: every lane group owns elements (the Huffman bound needs 32 group maxima)
+bool stream_ok(const ns_codec_params* p) { return p->V >= 4 * CT && getenv("NS_CODEC_STREAM_OFF") == nullptr; }
+
 template <typename K>
 int launch_codec(K kernel, const ns_codec_params* p, int smem, bool* configured, void* stream) {
   if (!*configured && smem > 0) {
@@ -824,23 +839,28 @@ int row_smem(const ns_codec_params* p, bool huffman) {
 extern "C" {
 
 int ns_sizeof_codec_params(void) { return (int)sizeof(ns_codec_params); }
+
 const char* ns_codec_last_error_string(void) { return g_cerr; }
 
 int ns_rank_encode_step(const ns_codec_params* p, void* s) {
   int rc = validate_codec(p, K_RANK_ENC); if (rc) return rc;
+  if (stream_ok(p) && !(p->top_p > 0.0 && p->top_p < 1.0) && !(p->min_prob > 0.0)) return launch_stream_codec(codec_stream_kernel<K_RANK_ENC>, p, s);
   static bool c = false; return launch_codec(rank_kernel<false>, p, row_smem(p, false), &c, s);
 }
 int ns_rank_decode_step(const ns_codec_params* p, void* s) {
   int rc = validate_codec(p, K_RANK_DEC); if (rc) return rc;
+  if (stream_ok(p) && !(p->top_p > 0.0 && p->top_p < 1.0) && !(p->min_prob > 0.0)) return launch_stream_codec(codec_stream_kernel<K_RANK_DEC>, p, s);
   static bool c = false; return launch_codec(rank_kernel<true>, p, row_smem(p, false), &c, s);
 }
 int ns_huffman_encode_step(const ns_codec_params* p, void* s) {
   int rc = validate_codec(p, K_HUF_ENC); if (rc) return rc;
+  if (stream_ok(p) && p->param <= 5) return launch_stream_codec(codec_stream_kernel<K_HUF_ENC>, p, s);
   if (row_smem(p, true) > SMEM_LIMIT && p->param > 7) return cerr(NS_E_VOCAB, "bits_per_word > 7 needs a smaller vocabulary");
   static bool c = false; return launch_codec(huffman_kernel<false>, p, row_smem(p, p->param > 7), &c, s);
 }
 int ns_huffman_decode_step(const ns_codec_params* p, void* s) {
   int rc = validate_codec(p, K_HUF_DEC); if (rc) return rc;
+  if (stream_ok(p) && p->param <= 5) return launch_stream_codec(codec_stream_kernel<K_HUF_DEC>, p, s);
   if (row_smem(p, true) > SMEM_LIMIT && p->param > 7) return cerr(NS_E_VOCAB, "bits_per_word > 7 needs a smaller vocabulary");
   static bool c = false; return launch_codec(huffman_kernel<true>, p, row_smem(p, p->param > 7), &c, s);
 }
