@@ -22,7 +22,7 @@ constexpr int CW = CT / 32;
 constexpr int C_NB = 2048;                   // histogram buckets
 constexpr int C_BPT = C_NB / CT;
 constexpr int C_LIST = 512;
-constexpr int C_UNROLL = 4;                  // chunk loads in flight per thread
+template <int N> struct Depth { static constexpr int value = N; };   // chunk loads in flight per thread of a sweep
 
 constexpr int C_GROUPS = 32;                 // lane groups whose maxima bound the Huffman selection
 constexpr int C_GL = CT / C_GROUPS;          // lanes per group (8)
@@ -127,14 +127,15 @@ __global__ void __launch_bounds__(CT, 2) codec_stream_kernel(ns_codec_params P) 
   // Sweep over the row: the interior chunks 1 .. W4-2 with C_UNROLL straight 128-bit loads in flight per thread (no
   // branch between them), then the two edge chunks element-wise by two threads.  body(v, first id, edge): `edge` chunks
   // carry -inf outside the row.
-  auto sweep = [&](bool last, auto body) {
+  auto sweep = [&](bool last, auto body, auto depth) {
+    constexpr int U = decltype(depth)::value;                // loads in flight per thread
     int c = 1 + tid;
-    for (; c + (C_UNROLL - 1) * CT < W4 - 1; c += C_UNROLL * CT) {
-      float4 v[C_UNROLL];
+    for (; c + (U - 1) * CT < W4 - 1; c += U * CT) {
+      float4 v[U];
 #pragma unroll
-      for (int u = 0; u < C_UNROLL; ++u) v[u] = ldg4(c + u * CT, last);
+      for (int u = 0; u < U; ++u) v[u] = ldg4(c + u * CT, last);
 #pragma unroll
-      for (int u = 0; u < C_UNROLL; ++u) body(fold(v[u], c + u * CT), 4 * (c + u * CT) - mis, false);
+      for (int u = 0; u < U; ++u) body(fold(v[u], c + u * CT), 4 * (c + u * CT) - mis, false);
     }
     for (; c < W4 - 1; c += CT) body(fold(ldg4(c, last), c), 4 * c - mis, false);
     if (tid == 0 || tid == 32) {
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(CT, 2) codec_stream_kernel(ns_codec_params P) 
     if (RANK)                                                // bucket range of the selection: keys above -1e9 (no -inf)
       lk = fminf(lk, fminf(fminf(v.x > -1e9f ? v.x : INFINITY, v.y > -1e9f ? v.y : INFINITY),
                            fminf(v.z > -1e9f ? v.z : INFINITY, v.w > -1e9f ? v.w : INFINITY)));
-  });
+  }, Depth<8>());   // from HBM: more bytes in flight
   {
     const unsigned gmask = ((1u << C_GL) - 1u) << (C_GL * (lane / C_GL));       // this lane's group of C_GL lanes
     const uint32_t a = __reduce_max_sync(gmask, ns_f32_orderable(bk));
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(CT, 2) codec_stream_kernel(ns_codec_params P) 
           else atomicAdd(&hist[stream_bin(k, scale, boff)], 1u);
         }
       }
-    });
+    }, Depth<4>());
     const u64 both = block_sum_u(((u64)before << 40) | (u64)cnt);
     const u64 total_pos = both & 0xffffffffffull;
     if (total_pos < n_pos) n_pos = total_pos;
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(CT, 2) codec_stream_kernel(ns_codec_params P) 
               if (s2 < C_LIST) { list[s2].pack = pack_of(xs[j], id + j); list[s2].w = 1; }
             }
           }
-        });
+        }, Depth<4>());
       }
       __syncthreads();
       int nl = sc.list_count;
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(CT, 2) codec_stream_kernel(ns_codec_params P) 
           if (v.z == mx) ti = min(ti, id + 2);
           if (v.y == mx) ti = min(ti, id + 1);
           if (v.x == mx) ti = min(ti, id);
-        });
+        }, Depth<4>());
         ti = __reduce_min_sync(0xffffffffu, ti);
         __syncthreads();
         if (lane == 0) sc.red[warp] = (u64)(uint32_t)ti;
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(CT, 2) codec_stream_kernel(ns_codec_params P) 
           }
         }
       }
-    });
+    }, Depth<4>());
     double sum = acc0 + acc1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
