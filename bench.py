@@ -52,51 +52,124 @@ def peaks():
 # ------------------------------------------------------------------------------------------
 # CPU codec (oracle port) -- baseline leg and --impl reference arm
 # ------------------------------------------------------------------------------------------
+_ROWS = None
+
+
+def _cpu_rows(seed):
+    global _ROWS
+    if _ROWS is None or _ROWS[0] != seed:
+        rng = np.random.Generator(np.random.PCG64(seed))
+        _ROWS = (seed, [rng.standard_normal(V, dtype=np.float32) * np.float32(3.0) for _ in range(4)],
+                 rng.integers(0, 2, MSG_BITS).tolist())
+    return _ROWS[1], _ROWS[2]
+
+
 def _cpu_worker(args):
-    seed, steps = args
+    """One stream of the CPU codec: `steps` tokens of leg `kind`; returns (tokens, bits, seconds)."""
+    seed, steps, kind = args
     from oracle import ac_oracle as O
-    rng = np.random.Generator(np.random.PCG64(seed))
-    rows = [rng.standard_normal(V, dtype=np.float32) * np.float32(3.0) for _ in range(4)]
-    msg = rng.integers(0, 2, MSG_BITS).tolist()
+    from oracle import codecs_oracle as K
+    rows, msg = _cpu_rows(seed)
+    fn = lambda t: rows[t % 4]
     t0 = time.perf_counter()
-    res = O.encode_stream(lambda t: rows[t % 4], msg, temp=TEMP, precision=PRECISION, topk=V,
-                          max_steps=steps, keep_trace=False)
-    return len(res.tokens), res.bits_consumed, time.perf_counter() - t0
+    if kind == "ac_encode_full":
+        res = O.encode_stream(fn, msg, temp=TEMP, precision=PRECISION, topk=V, max_steps=steps, keep_trace=False)
+        n, bits = len(res.tokens), res.bits_consumed
+    elif kind == "ac_encode_topk300":
+        res = O.encode_stream(fn, msg, temp=0.9, precision=PRECISION, topk=300, max_steps=steps, keep_trace=False)
+        n, bits = len(res.tokens), res.bits_consumed
+    elif kind == "ac_decode_full":
+        res = O.encode_stream(fn, msg, temp=TEMP, precision=PRECISION, topk=V, max_steps=steps, keep_trace=False)
+        t0 = time.perf_counter()                              # only the decode is timed
+        out, _ = O.decode_stream(fn, res.tokens, temp=TEMP, precision=PRECISION, topk=V)
+        n, bits = len(res.tokens), len(out)
+    elif kind == "huffman_b3":
+        toks, used = K.huffman_encode(fn, msg[: 3 * steps], 3)
+        n, bits = len(toks), used
+    elif kind == "bins_b3":
+        toks = K.bins_encode(fn, msg[: 3 * steps], 3, V)
+        toks = toks[0] if isinstance(toks, tuple) else toks
+        n, bits = len(toks), 3 * len(toks)
+    elif kind == "rank":
+        payload = bytes(np.packbits(np.asarray(msg[: 15 * steps + 8], dtype=np.uint8))[: (15 * steps) // 8])
+        toks, hist, total = K.rank_encode(fn, payload)
+        n, bits = len(toks), total
+    else:
+        raise ValueError(kind)
+    return n, bits, time.perf_counter() - t0
+
+
+class CpuCodec:
+    """All host cores, one independent stream per process (the reference codes one stream per call)."""
+
+    def __init__(self, procs):
+        import multiprocessing as mp
+        os.environ.setdefault("OMP_NUM_THREADS", "1")
+        self.procs = procs
+        self.pool = mp.get_context("fork").Pool(procs)
+
+    def run(self, steps_per_stream, kind="ac_encode_full"):
+        """-> (tokens/s, bits/s, tokens, wall seconds) of one bounded sample: `procs` streams x `steps_per_stream` tokens."""
+        t0 = time.perf_counter()
+        out = self.pool.map(_cpu_worker, [(100 + i, steps_per_stream, kind) for i in range(self.procs)])
+        wall = time.perf_counter() - t0
+        toks = sum(o[0] for o in out)
+        bits = sum(o[1] for o in out)
+        busy = max(o[2] for o in out)
+        return toks / busy, bits / busy, toks, wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
 def cpu_codec_throughput(steps_per_stream: int, procs: int):
-    """tokens/s of the CPU codec with `procs` independent streams in parallel."""
-    import multiprocessing as mp
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
-    ctx = mp.get_context("fork")
-    t0 = time.perf_counter()
-    with ctx.Pool(procs) as pool:
-        out = pool.map(_cpu_worker, [(100 + i, steps_per_stream) for i in range(procs)])
-    wall = time.perf_counter() - t0
-    toks = sum(o[0] for o in out)
-    bits = sum(o[1] for o in out)
-    busy = max(o[2] for o in out)
-    return toks / busy, bits / busy, toks, wall
+    c = CpuCodec(procs)
+    try:
+        return c.run(steps_per_stream)
+    finally:
+        c.close()
+
+
+def config_dict(B, strong=False):
+    return {"workload": WORKLOAD, "streams_per_gpu": B, "vocab": V, "precision": PRECISION, "temp": TEMP,
+            "topk": V, "l2": "inputs larger than L2: 4-entry logits pool, 823 MB per step",
+            "parallelism": "streams sharded over ranks, no collective in the loop"}
 
 
 def run_reference_arm(args):
+    """The reference's CPU codec on the box's host cores.  One step = one bounded sample of the workload: every core
+    codes `per` tokens of its own stream (the full 4096-stream step would take ~17 s per step on 16 cores);
+    `ms_per_step` is the measured wall time of such a step, `value` the tokens/s it amounts to."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per = max(64, 4 * args.steps)
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_codec_throughput(4, cores)
-    tps, bps, toks, wall = cpu_codec_throughput(per, cores)
+    per = 32
+    codec = CpuCodec(cores)
+    for _ in range(max(1, min(args.warmup, 2))):
+        codec.run(2)
+    steps = max(1, min(args.steps, 60))
+    toks = 0
+    bits = 0.0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tps_i, bps_i, n_i, wall_i = codec.run(per)
+        toks += n_i
+        bits += bps_i * (n_i / tps_i)
+    wall = time.perf_counter() - t0
+    codec.close()
+    tps = toks / wall
     line = {
         "impl": "reference", "metric": METRIC, "value": tps, "unit": "tokens/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * STREAMS / tps,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU codec = oracle port of code_base/arithmetic.py (the reference is "
-                   "not present on the GPU box); ms_per_step = time this host needs for one 4096-stream step"},
-        "message_bits_per_sec": bps,
+        "config": dict(config_dict(STREAMS), sample="one step = %d streams x %d encode steps (one process per core), a bounded "
+                       "sample of the 4096-stream step" % (cores, per),
+                       note="CPU codec = oracle port of code_base/arithmetic.py (the Python reference is not present on the GPU box)"),
+        "message_bits_per_sec": bits / wall,
         "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": cores, "kind": "port",
-                         "sample": "%d independent streams x %d encode steps, V=50257, one process per core" % (cores, per)},
+                         "sample": "%d steps of %d independent streams x %d encode steps, V=50257, one process per core" % (steps, cores, per)},
         "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -171,11 +244,19 @@ def run_gpu_arm(args):
     cores = os.cpu_count() or 1
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        ctps, cbps, ctoks, cwall = cpu_codec_throughput(args.cpu_steps, cores)
+        codec = CpuCodec(cores)
+        ctps, cbps, ctoks, cwall = codec.run(args.cpu_steps)
+        legs = {}
+        for kind, n in (("ac_decode_full", args.cpu_steps // 4), ("ac_encode_topk300", args.cpu_steps // 4),
+                        ("huffman_b3", args.cpu_steps // 4), ("bins_b3", args.cpu_steps // 8), ("rank", args.cpu_steps // 8)):
+            ltps, lbps, ltoks, lwall = codec.run(max(4, n), kind)
+            legs[kind] = {"tokens_per_sec": ltps, "bits_per_sec": lbps, "tokens": ltoks}
+        codec.close()
         cpu = {"value": ctps, "unit": "tokens/s", "cores": cores, "kind": "port",
                "message_bits_per_sec": cbps,
                "sample": "%d independent streams x %d encode steps of the same workload (V=50257, precision 26, "
-                         "full distribution), one process per core; %d tokens in %.1f s wall" % (cores, args.cpu_steps, ctoks, cwall)}
+                         "full distribution), one process per core; %d tokens in %.1f s wall" % (cores, args.cpu_steps, ctoks, cwall),
+               "legs": legs}
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the coder has no CPU fallback)")
     torch.cuda.set_device(local)
@@ -360,6 +441,39 @@ def run_gpu_arm(args):
         bits, live, rt_sum = [int(x) for x in cnt.tolist()]
         rt_ok = rt_sum == world
 
+    # config 2's shape end to end through the provider API: host bits in -> host tokens out (GPT-2-small-shaped random-init
+    # trunk in PyTorch + the coder at temp 0.9 / precision 26 / topk 300, whole loop under CUDA graphs)
+    generation = None
+    if rank == 0 and not args.no_generation:
+        del pool
+        torch.cuda.empty_cache()
+        from neuralsteganography_b200.lm import B200ArithmeticLM, random_init_model
+        gtok, gmodel = random_init_model("gpt2", seed=1234)
+        glm = B200ArithmeticLM(gmodel.to(dev), gtok, device=dev, max_len=512)
+        gB, gbits = args.gen_streams, 1024
+        grng = np.random.Generator(np.random.PCG64(7))
+        gmsgs = [grng.integers(0, 2, gbits).tolist() for _ in range(gB)]
+        gq = {"temp": 0.9, "precision": 26, "topk": 300, "finish_sent": False}
+        gctx = [50256, 464, 2068]
+        glm.encode_arithmetic_batch(gmsgs, gctx, quality=gq)                 # warm-up: graph capture, cuBLAS plans
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        covers = glm.encode_arithmetic_batch(gmsgs, gctx, quality=gq)
+        torch.cuda.synchronize()
+        t_enc = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        back = glm.decode_arithmetic_batch(covers, gctx, quality=gq)
+        torch.cuda.synchronize()
+        t_dec = time.perf_counter() - t0
+        ntok_g = sum(len(c) for c in covers)
+        generation = {"workload": "configs[1] shape: GPT-2-small random-init trunk (fp32), %d streams x %d message bits, temp 0.9, "
+                                  "precision 26, topk 300; B200ArithmeticLM.encode/decode_arithmetic_batch, host lists in and out" % (gB, gbits),
+                      "encode_tokens_per_sec": ntok_g / t_enc, "decode_tokens_per_sec": ntok_g / t_dec,
+                      "encode_message_bits_per_sec": gB * gbits / t_enc, "cover_tokens": ntok_g,
+                      "roundtrip_ok": all(b[:gbits] == m for b, m in zip(back, gmsgs))}
+        del glm, gmodel
+        torch.cuda.empty_cache()
+
     if rank == 0:
         tokens = world * B * K
         tps = tokens / (ms * 1e-3)
@@ -370,25 +484,24 @@ def run_gpu_arm(args):
             "metric": METRIC, "value": tps, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "streams_per_gpu": B, "vocab": V, "precision": PRECISION, "temp": TEMP,
-                       "topk": V, "l2": "inputs larger than L2: 4-entry logits pool, 823 MB per step",
-                       "parallelism": "streams sharded over ranks, no collective in the loop"},
+            "config": config_dict(B),
             "message_bits_per_sec": bits / (ms * 1e-3),
             "bits_per_token": bits / tokens,
             "decode_tokens_per_sec": tokens / (dms * 1e-3),
             "live_streams_at_end": live, "roundtrip_ok": bool(rt_ok),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_DRAM_BYTES_PER_TOKEN * B, "traffic_source": "ncu capture of 592 rows, scaled per row",
-                         "peak_source": peak_src, "kernel": "ac_fast_kernel<unit_temp, ENC>",
+                         "peak_source": peak_src, "kernel": "ac_duo_kernel<unit_temp, ENC>",
                          "algorithmic_bytes_per_token": ALGO_BYTES_PER_TOKEN},
             "cpu_baseline": cpu,
             "e2e": {"value": world * B * e2e_steps / (ems * 1e-3), "unit": "tokens/s",
                     "h2d_bytes_per_step": B * V * 4, "d2h_bytes_per_step": B * 4,
                     "note": "host logits (pinned) -> H2D -> ns_ac_encode_step -> tokens D2H, per rank; every step copies its own logits, the copy of step t+1 overlaps the coder step of step t (two device buffers)"},
-            "gpu_launches": 2 * K,   # per step: ac_fast_kernel + ac_step_kernel draining the hand-over queue
+            "gpu_launches": 2 * K,   # per step: ac_duo_kernel + ac_step_kernel draining the hand-over queue
             "gather_ms": gather_ms,
             "codecs": codecs,
             "topk300": topk_leg,
+            "generation": generation,
             "clocks": clocks,
         }
         print(json.dumps(line))
@@ -408,6 +521,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--codec-steps", type=int, default=8)
     ap.add_argument("--no-codecs", action="store_true")
+    ap.add_argument("--no-generation", action="store_true")
+    ap.add_argument("--gen-streams", type=int, default=256)
     ap.add_argument("--strong", action="store_true", help="strong scaling: --streams is the total over all ranks")
     args = ap.parse_args()
     if args.impl == "reference":
