@@ -34,7 +34,15 @@ for mode in ("enc", "dec"):
             for k, nm in enumerate(names[:11]):
                 print("   %-18s %8.0f cyc/row %5.1f%%" % (nm, q[k] / q[15], 100 * q[k] / q[:11].sum()))
         continue
+    if TOPK < V and os.environ.get("NS_AC_VARIANT", "0") != "2":
+        rnames = ["sweep 1 (HBM)", "reductions + bound", "sweep 2 (L2)", "rank-form check", "group listed keys", "order + exp + widths", "overfill + search + update"]
+        print(mode, "rank-form kernel: rows", int(pr[15]), "cycles/row (thread 0) %.0f" % (pr[:7].sum() / pr[15]))
+        for k, nm in enumerate(rnames):
+            print("   %-28s %8.0f" % (nm, pr[k] / pr[15]))
+        continue
     rows = pr[15]
+    if pr[11:15].any():
+        print("   (selection: locate %.0f, gather sweep %.0f, gather barrier %.0f, duplicates %.0f cycles/row; counted inside overfill/target sel: subtract)" % tuple(pr[11:15] / rows))
     print(mode, "rows", int(rows), "cycles/row total %.0f" % (pr[:11].sum() / rows))
     if pr[16:25].any():
         print("   piece arrival (cycles after row start, as seen by warp 1):", " ".join("%.0f" % (x / rows) for x in pr[16:25]))
