@@ -34,9 +34,10 @@ PRECISION = 26
 TEMP = 1.0
 MSG_BITS = 4096
 ALGO_BYTES_PER_TOKEN = 4 * V + 32          # SURVEY.md 8d / DESIGN.md
-# dram__bytes_read.sum + dram__bytes_write.sum of ac_fast_kernel from one `ncu --set full` capture
-# (592 rows: 119.27 MB + 7.20 MB, profiles/r1_final_fast_ncu_summary.txt), per row
-NCU_DRAM_BYTES_PER_TOKEN = (119269888 + 7197184) / 592
+# dram__bytes_read.sum + dram__bytes_write.sum of ac_lean_kernel<1, 0, 0> from one `ncu --set full` capture
+# (592 rows: 119.18 MB + 4.08 MB, profiles/r2a_lean_ncu_summary.txt), per row
+NCU_DRAM_BYTES_PER_TOKEN = (119176192 + 4079104) / 592
+NCU_TRAFFIC_SOURCE = "profiles/r2a_lean_ncu_summary.txt: ncu --set full capture of ac_lean_kernel<1,0,0> on 592 rows, scaled per row"
 METRIC = "coder_tokens_per_sec"
 WORKLOAD = "configs[2]: coder-only batch, 4096 streams x 50257 fp32 logits per GPU, full distribution, precision 26, temp 1.0"
 
@@ -490,14 +491,14 @@ def run_gpu_arm(args):
             "decode_tokens_per_sec": tokens / (dms * 1e-3),
             "live_streams_at_end": live, "roundtrip_ok": bool(rt_ok),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_DRAM_BYTES_PER_TOKEN * B, "traffic_source": "ncu capture of 592 rows, scaled per row",
-                         "peak_source": peak_src, "kernel": "ac_duo_kernel<unit_temp, ENC>",
+                         "traffic": NCU_DRAM_BYTES_PER_TOKEN * B, "traffic_source": NCU_TRAFFIC_SOURCE,
+                         "peak_source": peak_src, "kernel": "ac_lean_kernel<unit_temp, ENC> (csrc/ns_lean.cuh)",
                          "algorithmic_bytes_per_token": ALGO_BYTES_PER_TOKEN},
             "cpu_baseline": cpu,
             "e2e": {"value": world * B * e2e_steps / (ems * 1e-3), "unit": "tokens/s",
                     "h2d_bytes_per_step": B * V * 4, "d2h_bytes_per_step": B * 4,
                     "note": "host logits (pinned) -> H2D -> ns_ac_encode_step -> tokens D2H, per rank; every step copies its own logits, the copy of step t+1 overlaps the coder step of step t (two device buffers)"},
-            "gpu_launches": 2 * K,   # per step: ac_duo_kernel + ac_step_kernel draining the hand-over queue
+            "gpu_launches": 2 * K,   # per step: ac_lean_kernel + ac_step_kernel draining the hand-over queue
             "gather_ms": gather_ms,
             "codecs": codecs,
             "topk300": topk_leg,
