@@ -115,9 +115,8 @@ typedef struct ns_ac_params {
   void* scratch;
   int64_t scratch_stride;
   int32_t scratch_slots;
-  /* Kernel choice for the throughput path: 0 = default (threshold form of the cutoff: two rows in flight per SM, one
-     in shared memory and one in tensor memory, when V fits ns_ac_duo_max_vocab(); rank form and everything else: one
-     row per SM in shared memory), 2 = always the single-row kernel.  Results are identical. */
+  /* Kernel choice for the throughput path: 0 = default (threshold form of the cutoff: the lean single-row kernel
+     ns_lean.cuh; rank form, topk <= 512: ns_fast.cuh), 2 = always ns_fast.cuh.  Results are identical. */
   int32_t variant;
 } ns_ac_params;
 
@@ -128,7 +127,6 @@ int ns_sizeof_ac_params(void);
 /* largest V the arithmetic-coder kernels accept on this build (the row lives in shared memory) */
 int ns_ac_max_vocab(void);
 /* largest V the two-row kernel accepts (it needs a second scratch set beside the shared-memory row) */
-int ns_ac_duo_max_vocab(void);
 
 /* one encode step for B streams (code_base/arithmetic.py:114-210 loop body) */
 int ns_ac_encode_step(const ns_ac_params* p, void* cuda_stream);

@@ -20,7 +20,7 @@ PHASE_CODING, PHASE_TAIL, PHASE_DONE = 0, 1, 2
 ST_OUT_OF_RANGE, ST_BIN_OVERFLOW, ST_EST_RETRY, ST_TOKEN_OVERFLOW = 1, 2, 4, 8
 
 EXPORTS = (
-    "ns_version", "ns_last_error_string", "ns_ac_max_vocab", "ns_ac_duo_max_vocab",
+    "ns_version", "ns_last_error_string", "ns_ac_max_vocab",
     "ns_ac_encode_step", "ns_ac_decode_step", "ns_ac_debug_bins",
     "ns_rank_encode_step", "ns_rank_decode_step",
     "ns_huffman_encode_step", "ns_huffman_decode_step",
@@ -89,7 +89,6 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.ns_version.restype = C.c_int
     lib.ns_last_error_string.restype = C.c_char_p
     lib.ns_ac_max_vocab.restype = C.c_int
-    lib.ns_ac_duo_max_vocab.restype = C.c_int
     lib.ns_sizeof_ac_params.restype = C.c_int
     if hasattr(lib, "ns_sizeof_codec_params"):
         lib.ns_sizeof_codec_params.restype = C.c_int

@@ -462,18 +462,10 @@ namespace nsf_smem {
 #undef NSF_FT
 #undef NSF_MIN_CTAS
 }  // namespace nsf_smem
-// rank form of the cutoff (top-k binds, topk <= 512): no resident row, two sweeps from global memory
-namespace nsr {
-#include "ns_rankform.cuh"
-}  // namespace nsr
 // lean threshold-form kernel: one 1024-thread CTA per SM, one tight loop per sweep
 namespace nsl {
 #include "ns_lean.cuh"
 }  // namespace nsl
-// two rows in flight per SM: one in shared memory, one in tensor memory (threshold form of the cutoff)
-namespace nsd {
-#include "ns_duo.cuh"
-}  // namespace nsd
 
 // ------------------------------------------------------------------------------------
 // host side
@@ -552,14 +544,6 @@ int launch_fast(const ns_ac_params* p, cudaStream_t st) {
   return check_launch();
 }
 
-// rank-form kernel: one 512-thread CTA per row, two per SM
-template <bool UNIT, int MODE>
-int launch_rankform(const ns_ac_params* p, cudaStream_t st) {
-  if (p->B == 0) return NS_OK;
-  nsr::ac_rankform_kernel<UNIT, MODE><<<p->B, nsr::RT, 0, st>>>(*p, p->slow_ws);
-  return check_launch();
-}
-
 // lean kernel: persistent, one 1024-thread CTA per SM
 template <bool UNIT, int MODE>
 int launch_lean(const ns_ac_params* p, cudaStream_t st) {
@@ -576,20 +560,6 @@ int launch_lean(const ns_ac_params* p, cudaStream_t st) {
   return check_launch();
 }
 
-// two-row kernel: persistent, one 512-thread CTA per SM = two 8-warp groups with a row each
-template <bool UNIT, int MODE>
-int launch_duo(const ns_ac_params* p, cudaStream_t st) {
-  const int smem = nsd::D_FIXED + (p->V + 8) * 4;
-  static bool configured = false;
-  int rc = configure(nsd::ac_duo_kernel<UNIT, MODE>, &configured);
-  if (rc != NS_OK) return rc;
-  if (p->B == 0) return NS_OK;
-  const int sms = num_sms();
-  const int grid = (p->B + 1) / 2 < sms ? (p->B + 1) / 2 : sms;
-  nsd::ac_duo_kernel<UNIT, MODE><<<grid, 2 * nsd::GT, smem, st>>>(*p, p->slow_ws);
-  return check_launch();
-}
-
 template <int MODE>
 int dispatch(const ns_ac_params* p, u64* dbg_q, u64* dbg_meta, void* stream) {
   int rc = validate(p, MODE);
@@ -603,12 +573,8 @@ int dispatch(const ns_ac_params* p, u64* dbg_q, u64* dbg_meta, void* stream) {
   constexpr int M2 = MODE == MODE_DEBUG ? MODE_ENC : MODE;
   const bool rank = p->topk >= 2 && p->topk < p->V && p->topk <= nsf_smem::F_K_CAP;
   const bool lean = !rank && p->variant == 0 && p->V >= nsl::L_MIN_VOCAB && p->V <= nsl::L_MAX_VOCAB;
-  const bool duo = !rank && !lean && p->variant != 2 && p->V >= nsd::D_MIN_VOCAB && p->V <= nsd::D_MAX_VOCAB;
-  const bool rank_stream = rank && p->variant == 3 && p->V >= nsr::R_MIN_VOCAB;   // opt-in: measured slower (8.7 vs 10.1 M tok/s)
-  if (rank_stream) rc = (p->temp == 1.0) ? launch_rankform<true, M2>(p, st) : launch_rankform<false, M2>(p, st);
-  else if (rank) rc = (p->temp == 1.0) ? launch_fast<true, M2, true>(p, st) : launch_fast<false, M2, true>(p, st);
+  if (rank) rc = (p->temp == 1.0) ? launch_fast<true, M2, true>(p, st) : launch_fast<false, M2, true>(p, st);
   else if (lean) rc = (p->temp == 1.0) ? launch_lean<true, M2>(p, st) : launch_lean<false, M2>(p, st);
-  else if (duo) rc = (p->temp == 1.0) ? launch_duo<true, M2>(p, st) : launch_duo<false, M2>(p, st);
   else rc = (p->temp == 1.0) ? launch_fast<true, M2, false>(p, st) : launch_fast<false, M2, false>(p, st);
   if (rc != NS_OK) return rc;
   return launch_exact<MODE, uint32_t>(p, dbg_q, dbg_meta, p->slow_ws, st);
@@ -621,7 +587,6 @@ extern "C" {
 int ns_version(void) { return NS_ABI_VERSION; }
 const char* ns_last_error_string(void) { return g_err; }
 int ns_ac_max_vocab(void) { return MAX_VOCAB; }
-int ns_ac_duo_max_vocab(void) { return nsd::D_MAX_VOCAB; }
 int ns_sizeof_ac_params(void) { return (int)sizeof(ns_ac_params); }
 
 int ns_ac_encode_step(const ns_ac_params* p, void* cuda_stream) { return dispatch<MODE_ENC>(p, nullptr, nullptr, cuda_stream); }

@@ -722,8 +722,9 @@ __device__ __forceinline__ void lean_row(const ns_ac_params& P, int32_t* slow_ws
         }
         // dummies (width 0) land in 32 per-lane buckets of the wrapped index: no same-address serialisation
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < 4; ++j) {
           asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(hb | (((L_TOP - bt[j]) >> sh2) & ((uint32_t)(L_NB - 1) << 2))), "r"(q[j]) : "memory");
+        }
       }
     }
     if (pend0 >= 0) {
@@ -826,34 +827,29 @@ __device__ __forceinline__ void lean_row(const ns_ac_params& P, int32_t* slow_ws
     if (last) next_row_copy();
     const int n = sc->c_n;
     if (n > L_C_CAP) { overflow = true; return false; }
-    // entries sharing a packed e (rare with 24 mantissa bits) need the original logit to be ordered
-    {
-      const int c = tid >> 2, sub = tid & 3;
-      int d = 0;
-      if (c < n) {
-        const uint32_t eb = clist[c].ebits;
-        for (int o = sub; o < n; o += 4) d |= (int)((o != c) && (clist[o].ebits == eb));
-      }
-      d |= __shfl_xor_sync(0xffffffffu, d, 1);
-      d |= __shfl_xor_sync(0xffffffffu, d, 2);
-      if (d && sub == 0) clist[c].key = g[clist[c].id] + 0.0f;
-      if (__syncthreads_or(d)) { /* keys are visible */ }
-    }
-    pc.mark(14);
-    // coder order: larger e first; equal truncated e: larger logit first; equal logits: lower id first.
-    // Four lanes share one entry, each scans every fourth other entry; integer sums, any order.
+    // coder order: larger e first; equal truncated e (rare with 24 mantissa bits): larger original logit first, fetched
+    // on demand; equal logits: lower id first.  Four lanes share one entry, each scans every fourth other entry.
     {
       const int c = tid >> 2, sub = tid & 3;
       const bool live = c < n;
       LCand me = {0u, 0, 0u, 0.f};
       if (live) me = clist[c];
       u64 before = 0;
-      if (live)
+      if (live) {
+        float mkey = 0.f; bool have = false;
         for (int o = sub; o < n; o += 4) {
           const LCand ot = clist[o];
-          const bool b4 = (ot.ebits != me.ebits) ? (ot.ebits > me.ebits) : (ot.key != me.key) ? (ot.key > me.key) : (ot.id < me.id);
-          if (o != c && b4) before += ot.w;
+          bool b4;
+          if (ot.ebits != me.ebits) b4 = ot.ebits > me.ebits;
+          else if (o == c) b4 = false;
+          else {
+            if (!have) { mkey = g[me.id] + 0.0f; have = true; }
+            const float okey = g[ot.id] + 0.0f;
+            b4 = (okey != mkey) ? (okey > mkey) : (ot.id < me.id);
+          }
+          if (b4) before += ot.w;
         }
+      }
       before += __shfl_xor_sync(0xffffffffu, before, 1);
       before += __shfl_xor_sync(0xffffffffu, before, 2);
       before += pref;
@@ -862,6 +858,7 @@ __device__ __forceinline__ void lean_row(const ns_ac_params& P, int32_t* slow_ws
         sc->res_found = 1;
       }
     }
+    pc.mark(14);
     __syncthreads();
     return sc->res_found != 0;
   };

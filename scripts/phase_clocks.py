@@ -25,7 +25,7 @@ for mode in ("enc", "dec"):
     for t in range(3): step(pool[t % P])
     torch.cuda.synchronize()
     pr = st.prof.cpu().numpy().astype(np.float64)
-    if os.environ.get("DUO", "1") == "1" and TOPK >= V:
+    if False:
         for gi, gname in enumerate(("group 0 (row in shared memory)", "group 1 (row in tensor memory)")):
             q = pr[16 * gi: 16 * gi + 16]
             if q[15] == 0:
