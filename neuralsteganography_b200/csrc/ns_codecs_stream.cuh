@@ -33,9 +33,12 @@ struct StreamScal {
   u64 sel_prefix;
 };
 
-// monotone bucket of a key without a conversion instruction: (m - k) * scale rounded by the 2^23 trick, clamped to [0, NB)
-__device__ __forceinline__ int stream_bin(float k, float scale, float off) {
-  return __float_as_int(fmaxf(fminf(fmaf(-k, scale, off), 8388608.0f + (float)(C_NB - 1)), 8388608.0f)) & (C_NB - 1);
+// monotone bucket of a key without a conversion or a shift: (hi - k) * scale + 2^21 lands in [2^21, 2^22), where a float
+// counts quarters -- its mantissa field is rint(4 (hi - k) scale), and that field with the two low bits masked off is
+// the BYTE offset of bucket floor((hi - k) scale + 1/8) in the histogram.  Clamped to [0, NB) buckets.
+constexpr float C_MAGIC = 2097152.0f;        // 2^21
+__device__ __forceinline__ uint32_t stream_off(float k, float scale, float off) {
+  return __float_as_uint(fmaxf(fminf(fmaf(-k, scale, off), C_MAGIC + (float)(C_NB - 1) + 0.75f), C_MAGIC)) & ((uint32_t)(C_NB - 1) << 2);
 }
 
 // Huffman tree of n <= 32 leaves by one warp: while all frequencies met so far are distinct, "pop the two smallest" has
@@ -115,6 +118,7 @@ __global__ void __launch_bounds__(CT, 2) codec_stream_kernel(ns_codec_params P) 
     return v;
   };
   auto fold = [&](float4 v, int c) -> float4 {               // -0 -> +0; forbidden tokens (huffman_baseline.py:26-27)
+    if (RANK) return v;                                      // the rank codec compares floats (-0 == +0) and folds where it packs a key
     v.x += 0.0f; v.y += 0.0f; v.z += 0.0f; v.w += 0.0f;
     if (USE_MASK && (c == mc0 || c == mc1)) {
       const int b = 4 * c - mis;
@@ -150,25 +154,81 @@ __global__ void __launch_bounds__(CT, 2) codec_stream_kernel(ns_codec_params P) 
   };
   if (RANK && !DECODE) for (int i = tid; i < C_NB; i += CT) hist[i] = 0;
   if (tid == 0) sc.list_count = 0;
-  // ---- sweep 1 (HBM): the extent
-  float bk = -INFINITY, lk = INFINITY;
-  sweep(false, [&](const float4 v, int, bool) {
+  // ---- rank encode: bucket range of the selection from a SAMPLE of the row (one chunk per thread, 8 KB), so that the
+  // count histogram is filled by the same sweep that takes the exact extent.  Any monotone bucket function gives the
+  // same token (the order inside a bucket is resolved exactly); a range that misses the true extent only clamps a few
+  // keys into the end buckets.
+  float scale = 0.0f, boff = C_MAGIC;
+  if (RANK && !DECODE) {
+    float sb = -INFINITY, sl = INFINITY;
+    const int stride = (W4 - 2) / CT > 0 ? (W4 - 2) / CT : 1;
+    const int cs = 1 + tid * stride;
+    if (cs < W4 - 1) {
+      const float4 v = fold(ldg4(cs, false), cs);
+      sb = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+      sl = fminf(fminf(v.x > -1e9f ? v.x : INFINITY, v.y > -1e9f ? v.y : INFINITY),
+                 fminf(v.z > -1e9f ? v.z : INFINITY, v.w > -1e9f ? v.w : INFINITY));
+    }
+    const uint32_t a = __reduce_max_sync(0xffffffffu, ns_f32_orderable(sb));
+    const uint32_t b = __reduce_min_sync(0xffffffffu, ns_f32_orderable(sl));
+    if (lane == 0) sc.red[warp] = ((u64)a << 32) | (u64)b;
+    __syncthreads();
+    uint32_t ga = 0, gb = 0xffffffffu;
+#pragma unroll
+    for (int w = 0; w < CW; ++w) { const u64 r = sc.red[w]; ga = max(ga, (uint32_t)(r >> 32)); gb = min(gb, (uint32_t)r); }
+    float smax = key_of_pack((u64)ga << 32), smin = key_of_pack((u64)gb << 32);
+    if (!(smax > -3.0e38f) || !(smax < 3.0e38f) || !(smin > -3.0e38f) || !(smin < 3.0e38f)) { smax = 1.0f; smin = -1.0f; }
+    float span = smax - smin;
+    if (!(span > 0.0f)) span = 1.0f;
+    const float hi_p = smax + 0.25f * span, lo_p = smin - 0.25f * span;   // the sample misses the tails: widen
+    scale = (float)C_NB / (hi_p - lo_p);
+    boff = hi_p * scale + C_MAGIC;
+    if (!(scale > 0.0f) || !(scale < 3.0e38f) || !(fabsf(boff) < 3.0e38f)) { scale = 0.0f; boff = C_MAGIC; }
+    __syncthreads();                                         // sc.red is reused below
+  }
+  // ---- sweep 1 (HBM): the extent; rank: with it everything that does not need the extent -- the count histogram
+  // (encode), the tokens ranked before the observed one (decode)
+  float bk = -INFINITY, ak = INFINITY;
+  float tkey = INFINITY;
+  if (RANK && DECODE) {
+    if (tok >= 0 && tok < V) tkey = g[tok] + 0.0f;           // else: an unknown token counts as rank 0 (nothing ranks before +inf)
+    else tok = -1;
+  }
+  uint32_t cnt = 0, before = 0;
+  const uint32_t hb = (uint32_t)__cvta_generic_to_shared(hist);
+  sweep(RANK && DECODE, [&](const float4 v, int id, bool edge) {
     bk = fmaxf(bk, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
-    if (RANK)                                                // bucket range of the selection: keys above -1e9 (no -inf)
-      lk = fminf(lk, fminf(fminf(v.x > -1e9f ? v.x : INFINITY, v.y > -1e9f ? v.y : INFINITY),
-                           fminf(v.z > -1e9f ? v.z : INFINITY, v.w > -1e9f ? v.w : INFINITY)));
+    if (RANK) {
+      const float xs[4] = {v.x, v.y, v.z, v.w};
+      if (!edge) {
+        ak = fminf(ak, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (DECODE) before += (xs[j] > tkey || (xs[j] == tkey && id + j < tok)) ? 1u : 0u;   // coder order: key, then lower id
+          else asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(hb + stream_off(xs[j], scale, boff)), "r"(1u) : "memory");
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if ((unsigned)(id + j) >= (unsigned)V) continue;   // padding of the edge chunks is not a token
+          ak = fminf(ak, xs[j]);
+          if (DECODE) before += (xs[j] > tkey || (xs[j] == tkey && id + j < tok)) ? 1u : 0u;
+          else asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(hb + stream_off(xs[j], scale, boff)), "r"(1u) : "memory");
+        }
+      }
+    }
   }, Depth<8>());   // from HBM: more bytes in flight
   {
     const unsigned gmask = ((1u << C_GL) - 1u) << (C_GL * (lane / C_GL));       // this lane's group of C_GL lanes
     const uint32_t a = __reduce_max_sync(gmask, ns_f32_orderable(bk));
-    const uint32_t b = __reduce_min_sync(0xffffffffu, ns_f32_orderable(lk));
+    const uint32_t c = RANK ? __reduce_min_sync(0xffffffffu, ns_f32_orderable(ak)) : 0u;
     if (lane % C_GL == 0) sc.wmax[tid / C_GL] = a;
-    if (lane == 0) sc.wmin[warp] = b;
+    if (lane == 0) sc.wmin[warp] = c;
   }
   __syncthreads();
   const uint32_t gmax = __reduce_max_sync(0xffffffffu, sc.wmax[lane]);
-  const uint32_t gmin = __reduce_min_sync(0xffffffffu, sc.wmin[lane & (CW - 1)]);
-  const float mx = key_of_pack((u64)gmax << 32), mn = key_of_pack((u64)gmin << 32);
+  const uint32_t gall = __reduce_min_sync(0xffffffffu, sc.wmin[lane & (CW - 1)]);
+  const float mx = key_of_pack((u64)gmax << 32), amin = key_of_pack((u64)gall << 32);   // amin: smallest key of the row (rank)
 
   auto block_sum_u = [&](u64 v) -> u64 {
 #pragma unroll
@@ -183,45 +243,27 @@ __global__ void __launch_bounds__(CT, 2) codec_stream_kernel(ns_codec_params P) 
   };
 
   if (RANK) {
-    // tokens with p > 0 (codec/arithmetic.py:372): the fp64 softmax underflows below exp(-745)
+    // tokens with p > 0 (codec/arithmetic.py:372): the fp64 softmax underflows below exp(-745).  Every token of an
+    // ordinary row has p > 0 (its smallest key lies above the bound): the count is V; otherwise one more sweep counts --
+    // a float compare except within a hair of the bound, where the fp64 expression decides.
     const double dm = (double)mx / P.temp;
     u64 n_pos = P.topk > 0 ? (u64)P.topk : ~0ull;            // quality.py:76-81
     const float kc = (float)((dm - 745.0) * P.temp);
     const float margin = fmaxf(1e-3f, fabsf(kc) * 1e-5f);
     const float k_yes = kc + margin, k_no = kc - margin;
-    const float span = mx - mn;
-    const float scale = span > 0.0f ? (float)C_NB / span : 0.0f;
-    const float boff = mx * scale + 8388608.0f;
-    float tkey = INFINITY;
-    if (DECODE) {
-      if (tok >= 0 && tok < V) tkey = g[tok] + 0.0f;         // else: an unknown token counts as rank 0 (nothing ranks before +inf)
-      else tok = -1;
-    }
-    // the underflow test is a float compare except within a hair of the bound, where the fp64 expression decides
-    // (a branch that is practically never taken)
-    uint32_t cnt = 0, before = 0;
-    sweep(DECODE, [&](const float4 v, int id, bool edge) {
-      const float xs[4] = {v.x, v.y, v.z, v.w};
-      const float lo4 = fminf(fminf(v.x, v.y), fminf(v.z, v.w));
-      if (!edge && lo4 > k_yes) {                            // the usual chunk: every token has p > 0
-        cnt += 4u;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (DECODE) before += (xs[j] > tkey || (xs[j] == tkey && id + j < tok)) ? 1u : 0u;   // coder order: key, then lower id
-          else atomicAdd(&hist[stream_bin(xs[j], scale, boff)], 1u);
-        }
-      } else {
+    if (amin > k_yes) cnt = tid == 0 ? (uint32_t)V : 0u;
+    else {
+      sweep(DECODE, [&](const float4 v, int id, bool) {
+        const float xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float k = xs[j];
-          if ((unsigned)(id + j) >= (unsigned)V) continue;   // padding of the edge chunks is not a token
+          if ((unsigned)(id + j) >= (unsigned)V) continue;
           if (k > k_yes) cnt += 1u;
           else if (k >= k_no) cnt += (((double)k / P.temp - dm) >= -745.0) ? 1u : 0u;
-          if (DECODE) before += (k > tkey || (k == tkey && id + j < tok)) ? 1u : 0u;
-          else atomicAdd(&hist[stream_bin(k, scale, boff)], 1u);
         }
-      }
-    }, Depth<4>());
+      }, Depth<4>());
+    }
     const u64 both = block_sum_u(((u64)before << 40) | (u64)cnt);
     const u64 total_pos = both & 0xffffffffffull;
     if (total_pos < n_pos) n_pos = total_pos;
@@ -260,14 +302,23 @@ __global__ void __launch_bounds__(CT, 2) codec_stream_kernel(ns_codec_params P) 
       if (tb >= 0) {
         // keys of bucket tb lie within one bucket width of its centre: a two-instruction test per element, the exact
         // bucket function only for those that pass
-        const float centre = scale > 0.0f ? mx - ((float)tb) / scale : mx, reach = scale > 0.0f ? 1.5f / scale : INFINITY;
+        // bucket tb holds the keys with (hi - k) scale in [tb - 1/8, tb + 7/8) (hi = the rounded offset of the bucket
+        // function); the end buckets also hold everything the range clamps.  One test per chunk, the exact bucket
+        // function only for the chunks that pass.
+        const float hi_p = (boff - C_MAGIC) / (scale > 0.0f ? scale : 1.0f);
+        const bool endb = tb == 0 || tb == C_NB - 1;
+        const float centre = scale > 0.0f ? hi_p - ((float)tb + 0.375f) / scale : mx, reach = (scale > 0.0f && !endb) ? 1.0f / scale : INFINITY;
+        const uint32_t tboff = (uint32_t)tb << 2;
         sweep(true, [&](const float4 v, int id, bool) {
-          const float xs[4] = {v.x, v.y, v.z, v.w};
+          const float near = fminf(fminf(fabsf(v.x - centre), fabsf(v.y - centre)), fminf(fabsf(v.z - centre), fabsf(v.w - centre)));
+          if (near <= reach) {
+            const float xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (fabsf(xs[j] - centre) <= reach && stream_bin(xs[j], scale, boff) == tb && (unsigned)(id + j) < (unsigned)V) {
-              const int s2 = atomicAdd(&sc.list_count, 1);
-              if (s2 < C_LIST) { list[s2].pack = pack_of(xs[j], id + j); list[s2].w = 1; }
+            for (int j = 0; j < 4; ++j) {
+              if (stream_off(xs[j], scale, boff) == tboff && (unsigned)(id + j) < (unsigned)V) {
+                const int s2 = atomicAdd(&sc.list_count, 1);
+                if (s2 < C_LIST) { list[s2].pack = pack_of(xs[j] + 0.0f, id + j); list[s2].w = 1; }
+              }
             }
           }
         }, Depth<4>());
