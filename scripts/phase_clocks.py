@@ -25,15 +25,6 @@ for mode in ("enc", "dec"):
     for t in range(3): step(pool[t % P])
     torch.cuda.synchronize()
     pr = st.prof.cpu().numpy().astype(np.float64)
-    if False:
-        for gi, gname in enumerate(("group 0 (row in shared memory)", "group 1 (row in tensor memory)")):
-            q = pr[16 * gi: 16 * gi + 16]
-            if q[15] == 0:
-                continue
-            print(mode, gname, "rows", int(q[15]), "cycles/row total %.0f" % (q[:11].sum() / q[15]))
-            for k, nm in enumerate(names[:11]):
-                print("   %-18s %8.0f cyc/row %5.1f%%" % (nm, q[k] / q[15], 100 * q[k] / q[:11].sum()))
-        continue
     if TOPK < V and os.environ.get("NS_AC_VARIANT", "0") != "2":
         rnames = ["sweep 1 (HBM)", "reductions + bound", "sweep 2 (L2)", "rank-form check", "group listed keys", "order + exp + widths", "overfill + search + update"]
         print(mode, "rank-form kernel: rows", int(pr[15]), "cycles/row (thread 0) %.0f" % (pr[:7].sum() / pr[15]))
@@ -41,9 +32,11 @@ for mode in ("enc", "dec"):
             print("   %-28s %8.0f" % (nm, pr[k] / pr[15]))
         continue
     rows = pr[15]
+    if TOPK >= V:      # lean kernel: slots 11..14 are the steps inside the selection (not part of the sum above them)
+        names[11:15] = ["  sel: locate bucket", "  sel: gather sweep", "  sel: gather barrier", "  sel: order candidates"]
     if pr[11:15].any():
-        print("   (selection: locate %.0f, gather sweep %.0f, gather barrier %.0f, duplicates %.0f cycles/row; counted inside overfill/target sel: subtract)" % tuple(pr[11:15] / rows))
-    print(mode, "rows", int(rows), "cycles/row total %.0f" % (pr[:11].sum() / rows))
+        print("   (slots 11-14 are timed separately: a row is the sum of all lines below)")
+    print(mode, "rows", int(rows), "cycles/row total %.0f" % (pr[:15].sum() / rows))
     if pr[16:25].any():
         print("   piece arrival (cycles after row start, as seen by warp 1):", " ".join("%.0f" % (x / rows) for x in pr[16:25]))
     if pr[25:29].any():
@@ -51,4 +44,4 @@ for mode in ("enc", "dec"):
     for k, nm in enumerate(names):
         if k >= 11 and pr[k] == 0:
             continue
-        print("   %-18s %8.0f cyc/row %5.1f%%" % (nm, pr[k] / rows, 100 * pr[k] / pr[:11].sum()))
+        print("   %-18s %8.0f cyc/row %5.1f%%" % (nm, pr[k] / rows, 100 * pr[k] / pr[:15].sum()))
