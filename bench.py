@@ -35,9 +35,9 @@ TEMP = 1.0
 MSG_BITS = 4096
 ALGO_BYTES_PER_TOKEN = 4 * V + 32          # SURVEY.md 8d / DESIGN.md
 # dram__bytes_read.sum + dram__bytes_write.sum of ac_lean_kernel<1, 0, 0> from one `ncu --set full` capture
-# (592 rows: 119.18 MB + 4.08 MB, profiles/r2a_lean_ncu_summary.txt), per row
-NCU_DRAM_BYTES_PER_TOKEN = (119176192 + 4079104) / 592
-NCU_TRAFFIC_SOURCE = "profiles/r2a_lean_ncu_summary.txt: ncu --set full capture of ac_lean_kernel<1,0,0> on 592 rows, scaled per row"
+# (592 rows: 119.20 MB + 3.97 MB, profiles/r2_lean_ncu_summary.txt), per row
+NCU_DRAM_BYTES_PER_TOKEN = (119200256 + 3966464) / 592
+NCU_TRAFFIC_SOURCE = "profiles/r2_lean_ncu_summary.txt: ncu --set full capture of ac_lean_kernel<1,0,0> on 592 rows, scaled per row"
 METRIC = "coder_tokens_per_sec"
 WORKLOAD = "configs[2]: coder-only batch, 4096 streams x 50257 fp32 logits per GPU, full distribution, precision 26, temp 1.0"
 
@@ -456,7 +456,8 @@ def run_gpu_arm(args):
         gmsgs = [grng.integers(0, 2, gbits).tolist() for _ in range(gB)]
         gq = {"temp": 0.9, "precision": 26, "topk": 300, "finish_sent": False}
         gctx = [50256, 464, 2068]
-        glm.encode_arithmetic_batch(gmsgs, gctx, quality=gq)                 # warm-up: graph capture, cuBLAS plans
+        gwarm = glm.encode_arithmetic_batch(gmsgs, gctx, quality=gq)         # warm-up: graph capture, cuBLAS plans
+        glm.decode_arithmetic_batch(gwarm, gctx, quality=gq)                 # (both directions)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         covers = glm.encode_arithmetic_batch(gmsgs, gctx, quality=gq)
