@@ -468,11 +468,29 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
         t_dec = time.perf_counter() - t0
         ntok_g = sum(len(c) for c in covers)
+        # the same loop with the trunk's GEMMs on the tensor cores (TF32; encoder and decoder share the setting)
+        glm_t = B200ArithmeticLM(gmodel, gtok, device=dev, max_len=512, trunk_tf32=True)
+        gw = glm_t.encode_arithmetic_batch(gmsgs, gctx, quality=gq)
+        glm_t.decode_arithmetic_batch(gw, gctx, quality=gq)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        covers_t = glm_t.encode_arithmetic_batch(gmsgs, gctx, quality=gq)
+        torch.cuda.synchronize()
+        t_enc_t = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        back_t = glm_t.decode_arithmetic_batch(covers_t, gctx, quality=gq)
+        torch.cuda.synchronize()
+        t_dec_t = time.perf_counter() - t0
+        ntok_t = sum(len(c) for c in covers_t)
+        tf32_leg = {"encode_tokens_per_sec": ntok_t / t_enc_t, "decode_tokens_per_sec": ntok_t / t_dec_t, "cover_tokens": ntok_t,
+                    "roundtrip_ok": all(b[:gbits] == m for b, m in zip(back_t, gmsgs))}
+        del glm_t
         generation = {"workload": "configs[1] shape: GPT-2-small random-init trunk (fp32), %d streams x %d message bits, temp 0.9, "
                                   "precision 26, topk 300; B200ArithmeticLM.encode/decode_arithmetic_batch, host lists in and out" % (gB, gbits),
                       "encode_tokens_per_sec": ntok_g / t_enc, "decode_tokens_per_sec": ntok_g / t_dec,
                       "encode_message_bits_per_sec": gB * gbits / t_enc, "cover_tokens": ntok_g,
-                      "roundtrip_ok": all(b[:gbits] == m for b, m in zip(back, gmsgs))}
+                      "roundtrip_ok": all(b[:gbits] == m for b, m in zip(back, gmsgs)),
+                      "trunk_tf32": tf32_leg}
         del glm, gmodel
         torch.cuda.empty_cache()
 

@@ -85,16 +85,16 @@ __constant__ double c_lk[8] = {NS_512_OVER_LN2, -NS_LN2_512_HI, -NS_LN2_512_LO, 
 // n = 512 k + j scales by 2^k before the last fma (exact: powers of two commute with rounding, nothing underflows for
 // a >= -708).  `tab` = shared-window address of the table, 4 KB aligned.
 __device__ __forceinline__ double l_exp64(double a, uint32_t tab) {
-  const double magic = c_lk[6];
+  const double magic = 6755399441055744.0;                 // 1.5 * 2^52: low word zero, an immediate operand
   const double t = __fma_rn(a, c_lk[0], magic);
   const uint32_t n = (uint32_t)__double2loint(t);          // low word = rint(a * 512/ln2), two's complement
-  const double nd = __dsub_rn(t, magic);
+  const double nd = (double)(int)n;                        // = t - magic exactly; a conversion instead of an fp64-pipe slot
   double r = __fma_rn(nd, c_lk[1], a);
   r = __fma_rn(nd, c_lk[2], r);
   uint32_t tlo, thi;
   asm("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(tlo), "=r"(thi) : "r"(((n << 3) & 0xff8u) | tab));
   double q = __fma_rn(r, c_lk[3], c_lk[4]);
-  q = __fma_rn(q, r, c_lk[5]);
+  q = __fma_rn(q, r, 0.5);
   const double r2 = __dmul_rn(r, r);
   const double p = __fma_rn(q, r2, r);
   const double T = __hiloint2double((int)(thi + n * 2048u), (int)tlo);
@@ -247,10 +247,8 @@ __device__ __forceinline__ void lean_p1(uint4* w4, int W4, int tid, uint32_t tab
                                         float kappa_hi, float kappa_lo, uint32_t dummy, LScal* sc, LBand* band, int mis,
                                         double& acc_out, double& accl_out) {
   double acc = 0.0, accl = 0.0;
-  // band test, conservative (the exact test runs on the rare path): kappa_lo <= x < kappa_hi  =>  bits(x - kappa_lo) <= bits(w)
-  uint32_t band_w = __float_as_uint(kappa_hi - kappa_lo);
   // loop constants as opaque register values: rematerialising them inside the loop costs more than holding them
-  asm volatile("" : "+f"(clamp_key), "+r"(tab), "+r"(dummy), "+r"(band_w), "+r"(W4));
+  asm volatile("" : "+f"(clamp_key), "+r"(tab), "+r"(dummy), "+r"(W4));
   auto a_of = [&](float key) -> double {                    // (double(x)/temp) - (double(max)/temp), :128-130
     double x = (double)fmaxf(key, clamp_key);
     if (!UNIT_TEMP) x = __ddiv_rn(x, temp);
@@ -266,9 +264,12 @@ __device__ __forceinline__ void lean_p1(uint4* w4, int W4, int tid, uint32_t tab
     for (int j = 0; j < 4; ++j) {
       const double e = l_exp64(a_of(x[j]), tab);
       acc = __dadd_rn(acc, e);
-      accl = __fma_rn(e, x[j] < kappa_lo ? 1.0 : 0.0, accl);   // exact: e * {0,1} + acc
-      o[j] = x[j] >= kappa_hi ? l_pack_e(e) : dummy;
-      maybe |= __float_as_uint(x[j] - kappa_lo) <= band_w;
+      // accl = sum of everything not certainly kept (the guard band included): one compare serves the sum, the packing
+      // and, with a second one folded onto it, the band test
+      const bool hi = x[j] >= kappa_hi;
+      if (!hi) accl = __dadd_rn(accl, e);                    // one predicated add
+      o[j] = hi ? l_pack_e(e) : dummy;
+      maybe |= (!hi) & (x[j] >= kappa_lo);
     }
     w4[c] = make_uint4(o[0], o[1], o[2], o[3]);
     if (maybe) {                                             // rare: inside the guard band
@@ -508,8 +509,7 @@ __device__ __forceinline__ void lean_row(const ns_ac_params& P, int32_t* slow_ws
       const double band_scale = __hiloint2double((1023 + 52 - band_E) << 20, 0);   // 2^(52 - band_E)
       for (int k = lane; k < nband; k += 32) {
         const double e = band[k].e;
-        if ((e * inv) >= thr) band_kept_n += 1;              // p_i >= 1/range, :69
-        else band_cut_int += (u64)__double2ull_rz(e * band_scale);   // exact, order-free
+        if ((e * inv) >= thr) { band_kept_n += 1; band_cut_int += (u64)__double2ull_rz(e * band_scale); }   // the KEPT ones here
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -519,7 +519,7 @@ __device__ __forceinline__ void lean_row(const ns_ac_params& P, int32_t* slow_ws
     }
     const u64 cand = n_hi + (u64)band_kept_n;                // only counted when topk < V
     const double sum_bc = (double)band_cut_int * __hiloint2double((1023 - 52 + band_E) << 20, 0);
-    const double S = (sum_all - sum_lo) - sum_bc;            // sum of the kept e_i
+    const double S = (sum_all - sum_lo) + sum_bc;            // sum of the kept e_i (sum_lo holds the whole band)
     // kept set must have 2..topk members, else the reference switches to rank form (:75).  The row maximum has
     // e == 1 exactly and any other kept token has e >= thr * sum_all >= thr: "another token is kept" <=> S > 1 + thr/2.
     const bool form_ok = need_count ? (cand >= 2 && cand <= (u64)P.topk) : ((inv >= thr) && (S > 1.0 + 0.5 * thr));
@@ -723,7 +723,7 @@ __device__ __forceinline__ void lean_row(const ns_ac_params& P, int32_t* slow_ws
         // dummies (width 0) land in 32 per-lane buckets of the wrapped index: no same-address serialisation
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(hb | (((L_TOP - bt[j]) >> sh2) & ((uint32_t)(L_NB - 1) << 2))), "r"(q[j]) : "memory");
+          asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(hb | ((bt[j] >> sh2) & ((uint32_t)(L_NB - 1) << 2))), "r"(q[j]) : "memory");
         }
       }
     }
@@ -732,13 +732,13 @@ __device__ __forceinline__ void lean_row(const ns_ac_params& P, int32_t* slow_ws
       for (int t = 0; t < 2; ++t) {
         const int id = t == 0 ? pend0 : pend1;
         if (id < 0) continue;
-        atomicAdd(&hist[((L_TOP - words[id + mis]) >> SH) & (L_NB - 1)], exact_mass(id, C));
+        atomicAdd(&hist[(words[id + mis] >> SH) & (L_NB - 1)], exact_mass(id, C));
       }
     }
     if (pend_over) sc->bail = L_WHY_BUCKET;
     if (tid < nband && band_kept(tid)) {
       const double e = band[tid].e;
-      atomicAdd(&hist[((L_TOP - l_pack_e(e)) >> SH) & (L_NB - 1)], (uint32_t)__double2ll_rn(e * C));
+      atomicAdd(&hist[(l_pack_e(e) >> SH) & (L_NB - 1)], (uint32_t)__double2ll_rn(e * C));
     }
   }
   pc.mark(5);
@@ -746,7 +746,11 @@ __device__ __forceinline__ void lean_row(const ns_ac_params& P, int32_t* slow_ws
   if (sc->bail) { const int why = sc->bail; give_up(why); return; }   // the split did not verify (warp 1) / too many undecidable widths
 
   // ------------------------------------------------------------------ SEL: bucket scan (two buckets per thread)
-  const uint32_t h0 = hist[2 * tid], h1 = hist[2 * tid + 1];
+  // Bucket of a packed e: (bits >> SH) mod 2048 -- no subtraction in the sweep; the kept keys span fewer than 2048
+  // consecutive values of bits >> SH below top_v = L_TOP >> SH, so the residues are distinct.  The coder's order is
+  // descending keys: position p of that order is bucket (top_v - p) mod 2048; thread t scans positions 2t, 2t + 1.
+  const uint32_t top_v = L_TOP >> SH;
+  const uint32_t h0 = hist[(top_v - 2u * (uint32_t)tid) & (L_NB - 1)], h1 = hist[(top_v - 2u * (uint32_t)tid - 1u) & (L_NB - 1)];
   uint32_t hexcl;                                            // mass in all buckets before this thread's first one
   {
     const uint32_t tsum = h0 + h1;
@@ -788,9 +792,9 @@ __device__ __forceinline__ void lean_row(const ns_ac_params& P, int32_t* slow_ws
     const int tb = sc->sel_bin;
     const u64 pref = sc->sel_prefix;
     if (tb < 0) { __syncthreads(); if (last) next_row_copy(); return false; }
-    // gather bucket tb: packed e in (L_TOP - ((tb + 1) << SH), L_TOP - (tb << SH)]
+    // gather position tb of the order: packed e with bits >> SH == top_v - tb
     {
-      uint32_t first = L_TOP - (((uint32_t)tb + 1u) << SH) + 1u, width = 1u << SH;
+      uint32_t first = (top_v - (uint32_t)tb) << SH, width = 1u << SH;
       int W4o = W4;
       asm volatile("" : "+r"(W4o), "+r"(first), "+r"(width));
 #pragma unroll 1

@@ -71,7 +71,9 @@ class StegoGenerator:
         if self.codec == "rank" and not decode:          # codec/arithmetic.py:159-166: per-token consumption
             self.history.scatter_(1, last[:, None], coder.nbits[:, None])
         prev = coder.tokens[self._rows, last].long().clamp(min=0)      # finished streams feed a stale token
-        self.logits.copy_(self.trunk.step(prev, kv_len))
+        res = self.trunk.step(prev, kv_len, out=self.logits)           # fp32 trunk: lm_head writes self.logits, no [B, V] copy
+        if res.data_ptr() != self.logits.data_ptr():
+            self.logits.copy_(res)
 
     def _new_coder(self, token_cap: int, kw: dict):
         if self.codec == "ac":

@@ -145,12 +145,15 @@ class B200ArithmeticLM:
     codec = "ac"
 
     def __init__(self, model, tokenizer, *, device: Optional[str] = None, max_len: int = 1024, use_graph: bool = True,
-                 batch_size: Optional[int] = None):
+                 batch_size: Optional[int] = None, trunk_tf32: bool = False):
         """``batch_size`` pins the number of streams every trunk call runs with (shorter batches are padded with idle
         streams).  Encoder and decoder must see bit-identical logits, and the trunk's cuBLAS GEMMs pick their
         algorithm -- hence the fp32 summation order -- by batch shape: a cover encoded as one of N streams has to be
         decoded at the same N.  Within one provider instance that is automatic (a decode is padded to the batch of
-        the last encode); a process that only decodes passes the encoder's ``batch_size`` here."""
+        the last encode); a process that only decodes passes the encoder's ``batch_size`` here.
+
+        ``trunk_tf32`` runs the trunk's GEMMs (the ``lm_head`` projection above all) on the tensor cores in TF32: the
+        logits then differ from an fp32 trunk's in their low bits, so encoder and decoder must both set it."""
         if not torch.cuda.is_available():
             raise ConfigurationError("%s needs a CUDA device (there is no CPU fallback)" % type(self).__name__)
         self.model = model.eval()
@@ -159,6 +162,7 @@ class B200ArithmeticLM:
         self.max_len = int(max_len)
         self.use_graph = bool(use_graph)
         self.batch_size = int(batch_size) if batch_size else None
+        self.trunk_tf32 = bool(trunk_tf32)
         self._last_encode_batch: Optional[int] = None
         self._gens: Dict[tuple, object] = {}
         self._sent_end: Optional[torch.Tensor] = None
@@ -219,7 +223,7 @@ class B200ArithmeticLM:
             gen = StegoGenerator(self.model, batch, max_len=self.max_len, precision=int(q["precision"]),
                                  temp=float(q["temp"]), topk=int(q["topk"]), finish_sent=bool(q["finish_sent"]),
                                  sent_end=self._sentence_end_table() if q["finish_sent"] else None,
-                                 device=self.device, use_graph=self.use_graph)
+                                 device=self.device, use_graph=self.use_graph, trunk_tf32=self.trunk_tf32)
             self._gens = {key: gen}            # keep one (KV buffers are large)
         return gen
 
@@ -374,7 +378,7 @@ class B200RankLM(B200ArithmeticLM):
         gen = self._gens.get(key)
         if gen is None:
             gen = StegoGenerator(self.model, batch, max_len=self.max_len, temp=float(q["temp"]), codec="rank", codec_kw=ckw,
-                                 device=self.device, use_graph=self.use_graph)
+                                 device=self.device, use_graph=self.use_graph, trunk_tf32=self.trunk_tf32)
             self._gens = {key: gen}
         return gen
 

@@ -169,13 +169,13 @@ class StaticGPT2:
             b *= 2
         return min(b, self.T)
 
-    def step(self, tokens: torch.Tensor, kv_len: Optional[int] = None) -> torch.Tensor:
+    def step(self, tokens: torch.Tensor, kv_len: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Append ``tokens`` [B] (int64) at position ``length``; returns fp32 logits [B, V].  No host sync.
         ``kv_len`` (host int, >= length + 1): only that prefix of the KV buffers is attended to."""
         with _matmul_tf32(self.tf32):
-            return self._step(tokens, kv_len)
+            return self._step(tokens, kv_len, out)
 
-    def _step(self, tokens: torch.Tensor, kv_len: Optional[int] = None) -> torch.Tensor:
+    def _step(self, tokens: torch.Tensor, kv_len: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         B = self.B
         Tk = self.T if kv_len is None else int(kv_len)
         ar = self._arange_t[:Tk]
@@ -207,6 +207,8 @@ class StaticGPT2:
         self.length.add_(1)
         self._host_len = None                               # replayed under CUDA graphs: the host no longer knows the length
         x = F.layer_norm(x, (self.n_embd,), self.lnfw, self.lnfb, self.eps)
+        if out is not None and self.dtype == torch.float32:       # the lm_head GEMM writes the coder's logits buffer directly
+            return torch.matmul(x, self.lm_head.t(), out=out)
         return (x @ self.lm_head.t()).float().contiguous()
 
     def reset(self) -> None:

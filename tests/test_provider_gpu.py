@@ -139,3 +139,18 @@ def test_cut_at_eos_is_the_reference_break():
     cut = cut_at_eos(ids, tok)
     assert tok.decode(cut).endswith("<eos>") and "<eos>" not in tok.decode(cut[:-1])
     assert cut_at_eos(tok.encode("abcdef"), tok) == tok.encode("abcdef")
+
+
+def test_tensor_core_trunk_roundtrip_when_both_sides_set_it():
+    """``trunk_tf32=True``: the trunk's GEMMs (lm_head above all) run on the tensor cores.  The logits differ from an fp32
+    trunk's in their low bits, so the setting belongs to the channel: encoder and decoder both use it and the messages
+    come back; the coder step itself is unchanged (same kernels, same integers for the logits it is given)."""
+    from neuralsteganography_b200.lm import B200ArithmeticLM, IdTokenizer, bytes_to_bits_lsb
+    model = _model(vocab=50257, width=128, heads=4)
+    q = {"temp": 0.9, "precision": 26, "topk": 300, "finish_sent": False}
+    pk = [F.build_packet(bytes([7 * r + 1] * 24), msg_id="t", seq=r, total=4, cfg={"chunk_bytes": 24, "crc": True}) for r in range(4)]
+    lm = B200ArithmeticLM(model, IdTokenizer(50257), max_len=1024, trunk_tf32=True)
+    ctx = lm.encode_seed("9 8 7")
+    covers = lm.encode_arithmetic_batch([bytes_to_bits_lsb(p) for p in pk], ctx, quality=q)
+    back = lm.decode_arithmetic_batch(covers, ctx, quality=q)
+    assert [F.bits_to_bytes(b) for b in back] == pk
