@@ -35,8 +35,8 @@ TEMP = 1.0
 MSG_BITS = 4096
 ALGO_BYTES_PER_TOKEN = 4 * V + 32          # SURVEY.md 8d / DESIGN.md
 # dram__bytes_read.sum + dram__bytes_write.sum of ac_lean_kernel<1, 0, 0> from one `ncu --set full` capture
-# (592 rows: 119.20 MB + 3.97 MB, profiles/r2_lean_ncu_summary.txt), per row
-NCU_DRAM_BYTES_PER_TOKEN = (119200256 + 3966464) / 592
+# (592 rows: 119.18 MB + 3.87 MB, profiles/r2_lean_ncu_summary.txt), per row
+NCU_DRAM_BYTES_PER_TOKEN = (119176192 + 3870208) / 592
 NCU_TRAFFIC_SOURCE = "profiles/r2_lean_ncu_summary.txt: ncu --set full capture of ac_lean_kernel<1,0,0> on 592 rows, scaled per row"
 METRIC = "coder_tokens_per_sec"
 WORKLOAD = "configs[2]: coder-only batch, 4096 streams x 50257 fp32 logits per GPU, full distribution, precision 26, temp 1.0"

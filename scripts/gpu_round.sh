@@ -20,6 +20,9 @@ for w in $what; do
     ncu)      $small --no-codecs > $out/${tag}_plain2.log 2>&1 &&
               timeout 900 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-ac_lean_kernel} -s 4 -c 1 -f -o $out/${tag}_prof $small --no-codecs > $out/${tag}_ncu_full.log 2>&1
               tail -2 $out/${tag}_ncu_full.log ;;
+    ncu_rank) $small > $out/${tag}_plain3.log 2>&1 &&
+              timeout 900 ncu --set full --clock-control none --import-source on -k regex:codec_stream_kernel -s 6 -c 1 -f -o $out/${tag}_rank_prof $small > $out/${tag}_ncu_rank.log 2>&1
+              tail -2 $out/${tag}_ncu_rank.log ;;
     soak)     STREAMS=${SOAK_STREAMS:-1024} STEPS=${SOAK_STEPS:-40} timeout 900 python scripts/soak_fast_vs_exact.py > $out/${tag}_soak.txt 2>&1; tail -12 $out/${tag}_soak.txt ;;
   esac
 done
