@@ -6,7 +6,9 @@ check=0
 for name in "$@"; do
   if [ "$name" == "--check" ]; then check=1; continue; fi
   export NS_CODER_LIB=$PWD/gpurun_bin/libns_$name.so
-  if [ $check == 0 ]; then
+  if [ $check == 0 ] && [ -n "$AB_TOPK" ]; then
+    printf "%-8s " $name; timeout 240 python scripts/bench_topk.py 2>&1 | head -1
+  elif [ $check == 0 ]; then
     timeout 240 python bench.py --steps ${AB_STEPS:-40} --no-cpu-baseline --no-generation --no-codecs > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err
     python - $name <<'PY'
 import json, sys
