@@ -9,11 +9,14 @@
 // from global memory -- the first from HBM, the later ones from L2 (the row was just read; 148 SMs x 4 rows x 201 KB is
 // half of the 126 MB L2).  Rows in different phases share an SM, so HBM latency, L2 latency, barriers and the serial
 // tree / resolve steps of one row hide under the sweeps of the others.
-//   sweep 1  extent: largest and smallest key (-0 folded, forbidden tokens at -1e10 on the fly: the logits are read-only)
-//   sweep 2  Huffman: fp32 log_softmax normaliser + the few candidates of the top 2^b (bounded from below by the n-th
-//            largest warp maximum: no histogram); rank decode: tokens with p > 0 and tokens ranked before the observed
-//            one; rank encode: the same count + a count histogram (conversion-free bucket function)
-//   sweep 3  rank encode only: gather the bucket of the wanted position, resolve it exactly
+//   sweep 1  (HBM) extent: largest key (-0 folded, forbidden tokens at -1e10 on the fly: the logits are read-only), and with it
+//            everything that needs no extent -- rank encode: the count histogram of the selection, its bucket range taken
+//            from a SAMPLE of the row (one chunk per thread) because any monotone bucket function yields the same token;
+//            rank decode: the tokens ranked before the observed one (decode is done after this one sweep)
+//   sweep 2  (L2) Huffman: fp32 log_softmax normaliser + the few candidates of the top 2^b (bounded from below by the n-th
+//            largest group maximum: no histogram); rank encode: gather the bucket of the wanted position, resolve it exactly
+//   (rank)   the count of tokens with p > 0 is V whenever the row's smallest key lies above the fp64 underflow bound;
+//            only otherwise one more sweep counts them
 // Same integers as the row-resident kernels: selection by (key, lower id first).
 // Serves: Huffman with bits_per_word <= 5 (n <= 32 group maxima), rank without top_p / min_prob (top_k clamps the count).
 
@@ -275,55 +278,85 @@ __global__ void __launch_bounds__(CT, 2) codec_stream_kernel(ns_codec_params P) 
     }
     if (!DECODE) {
       const u64 index = (u64)(window >> (32 - capacity));                 // :153-157
-      // bucket of position `index`: scan of the count histogram
-      uint32_t hl[C_BPT], tsum = 0;
-#pragma unroll
-      for (int b = 0; b < C_BPT; ++b) { hl[b] = hist[tid * C_BPT + b]; tsum += hl[b]; }
-      uint32_t inc = tsum;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-      __syncthreads();
-      if (lane == 31) sc.red[warp] = inc;
-      if (tid == 0) { sc.sel_bin = -1; sc.sel_prefix = 0; sc.res_found = 0; }
-      __syncthreads();
-      uint32_t woff = 0;
-#pragma unroll
-      for (int w = 0; w < CW; ++w) if (w < warp) woff += (uint32_t)sc.red[w];
-      uint32_t excl = woff + inc - tsum;
-#pragma unroll
-      for (int b = 0; b < C_BPT; ++b) {
-        if (hl[b] != 0 && excl <= index && index < excl + hl[b]) { sc.sel_bin = tid * C_BPT + b; sc.sel_prefix = excl; }
-        excl += hl[b];
-      }
-      __syncthreads();
-      const int tb = sc.sel_bin;
-      const u64 prefix = sc.sel_prefix;
-      // sweep 3 (L2): gather that bucket
-      if (tb >= 0) {
-        // keys of bucket tb lie within one bucket width of its centre: a two-instruction test per element, the exact
-        // bucket function only for those that pass
-        // bucket tb holds the keys with (hi - k) scale in [tb - 1/8, tb + 7/8) (hi = the rounded offset of the bucket
-        // function); the end buckets also hold everything the range clamps.  One test per chunk, the exact bucket
-        // function only for the chunks that pass.
-        const float hi_p = (boff - C_MAGIC) / (scale > 0.0f ? scale : 1.0f);
-        const bool endb = tb == 0 || tb == C_NB - 1;
-        const float centre = scale > 0.0f ? hi_p - ((float)tb + 0.375f) / scale : mx, reach = (scale > 0.0f && !endb) ? 1.0f / scale : INFINITY;
-        const uint32_t tboff = (uint32_t)tb << 2;
-        sweep(true, [&](const float4 v, int id, bool) {
-          const float near = fminf(fminf(fabsf(v.x - centre), fabsf(v.y - centre)), fminf(fabsf(v.z - centre), fabsf(v.w - centre)));
-          if (near <= reach) {
-            const float xs[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (stream_off(xs[j], scale, boff) == tboff && (unsigned)(id + j) < (unsigned)V) {
-                const int s2 = atomicAdd(&sc.list_count, 1);
-                if (s2 < C_LIST) { list[s2].pack = pack_of(xs[j] + 0.0f, id + j); list[s2].w = 1; }
+      u64 prefix = 0;
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        // bucket of position `index`: scan of the count histogram
+        uint32_t hl[C_BPT], tsum = 0;
+  #pragma unroll
+        for (int b = 0; b < C_BPT; ++b) { hl[b] = hist[tid * C_BPT + b]; tsum += hl[b]; }
+        uint32_t inc = tsum;
+  #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        __syncthreads();
+        if (lane == 31) sc.red[warp] = inc;
+        if (tid == 0) { sc.sel_bin = -1; sc.sel_prefix = 0; sc.res_found = 0; }
+        __syncthreads();
+        uint32_t woff = 0;
+  #pragma unroll
+        for (int w = 0; w < CW; ++w) if (w < warp) woff += (uint32_t)sc.red[w];
+        uint32_t excl = woff + inc - tsum;
+  #pragma unroll
+        for (int b = 0; b < C_BPT; ++b) {
+          if (hl[b] != 0 && excl <= index && index < excl + hl[b]) { sc.sel_bin = tid * C_BPT + b; sc.sel_prefix = excl; }
+          excl += hl[b];
+        }
+        __syncthreads();
+        const int tb = sc.sel_bin;
+        prefix = sc.sel_prefix;
+        // sweep 3 (L2): gather that bucket
+        if (tb >= 0) {
+          // keys of bucket tb lie within one bucket width of its centre: a two-instruction test per element, the exact
+          // bucket function only for those that pass
+          // bucket tb holds the keys with (hi - k) scale in [tb - 1/8, tb + 7/8) (hi = the rounded offset of the bucket
+          // function); the end buckets also hold everything the range clamps.  One test per chunk, the exact bucket
+          // function only for the chunks that pass.
+          const float hi_p = (boff - C_MAGIC) / (scale > 0.0f ? scale : 1.0f);
+          const bool endb = tb == 0 || tb == C_NB - 1;
+          const float centre = scale > 0.0f ? hi_p - ((float)tb + 0.375f) / scale : mx, reach = (scale > 0.0f && !endb) ? 1.0f / scale : INFINITY;
+          const uint32_t tboff = (uint32_t)tb << 2;
+          sweep(true, [&](const float4 v, int id, bool) {
+            const float near = fminf(fminf(fabsf(v.x - centre), fabsf(v.y - centre)), fminf(fabsf(v.z - centre), fabsf(v.w - centre)));
+            if (near <= reach) {
+              const float xs[4] = {v.x, v.y, v.z, v.w};
+  #pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (stream_off(xs[j], scale, boff) == tboff && (unsigned)(id + j) < (unsigned)V) {
+                  const int s2 = atomicAdd(&sc.list_count, 1);
+                  if (s2 < C_LIST) { list[s2].pack = pack_of(xs[j] + 0.0f, id + j); list[s2].w = 1; }
+                }
               }
             }
-          }
+          }, Depth<4>());
+        }
+        __syncthreads();
+        if (sc.list_count <= C_LIST || attempt == 1) break;
+        // The sampled range put more keys into one bucket than the list holds (a row whose tail lies far outside the
+        // sample): once more with the exact extent, as many sweeps as it takes -- the row is in L2.
+        float lk = INFINITY;
+        sweep(false, [&](const float4 v, int, bool) {
+          lk = fminf(lk, fminf(fminf(v.x > -1e9f ? v.x : INFINITY, v.y > -1e9f ? v.y : INFINITY),
+                               fminf(v.z > -1e9f ? v.z : INFINITY, v.w > -1e9f ? v.w : INFINITY)));
         }, Depth<4>());
+        const uint32_t wl = __reduce_min_sync(0xffffffffu, ns_f32_orderable(lk));
+        __syncthreads();
+        if (lane == 0) sc.wmin[warp] = wl;
+        for (int i = tid; i < C_NB; i += CT) hist[i] = 0;
+        if (tid == 0) sc.list_count = 0;
+        __syncthreads();
+        const float mn = key_of_pack((u64)__reduce_min_sync(0xffffffffu, sc.wmin[lane & (CW - 1)]) << 32);
+        const float span = mx - mn;
+        scale = (span > 0.0f && span < 3.0e38f) ? (float)C_NB / span : 0.0f;
+        boff = mx * scale + C_MAGIC;
+        if (!(fabsf(boff) < 3.0e38f)) { scale = 0.0f; boff = C_MAGIC; }
+        sweep(false, [&](const float4 v, int id, bool edge) {
+          const float xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (!edge || (unsigned)(id + j) < (unsigned)V)
+              asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(hb + stream_off(xs[j], scale, boff)), "r"(1u) : "memory");
+        }, Depth<4>());
+        __syncthreads();
       }
-      __syncthreads();
       int nl = sc.list_count;
       if (nl > C_LIST) { nl = C_LIST; if (tid == 0 && P.status) atomicOr(&P.status[row], NS_ST_BIN_OVERFLOW); }
       if (tid < nl) {                                        // exact position inside the bucket

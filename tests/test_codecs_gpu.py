@@ -131,3 +131,33 @@ def test_get_bins_matches_reference_recipe():
     ob2w, ow2b = K.get_bins(50257, 3)
     assert np.array_equal(w2b, ow2b)
     assert all(np.array_equal(a, b) for a, b in zip(b2w, ob2w))
+
+
+def test_rank_encode_when_the_sampled_bucket_range_misses_the_row():
+    """The rank encoder takes its histogram range from a sample of the row (one chunk per thread).  Rows whose large keys
+    all lie outside the sampled chunks put them into one clamped end bucket; when the wanted position is in there the kernel
+    redoes the histogram with the exact extent.  Same tokens as the oracle, no overflow flag, and the cover decodes."""
+    V, B = 50257, 4
+    rng = np.random.default_rng(77)
+    base = rng.standard_normal((B, V)).astype(np.float32)
+    # 1500 outliers far above the bulk, none of them in a chunk the sample reads (chunks 1 + 24 t, t < 512, of aligned rows)
+    sampled = set()
+    for t in range(512):
+        c = 1 + t * ((((V + 3) >> 2) - 2) // 512)
+        sampled.update(range(4 * c - 4, 4 * c + 8))        # generous: any row misalignment 0..3
+    free = np.array([i for i in range(V) if i not in sampled])
+    for r in range(B):
+        ids = rng.choice(free, 1500, replace=False)
+        base[r, ids] = 100.0 + rng.permutation(1500).astype(np.float32) * 0.01
+    rows = torch.from_numpy(base).cuda()
+    fn = lambda t: rows
+    msgs = [[0] * 16 + message_bits(4100 + r, 32).tolist() for r in range(B)]     # leading zeros: positions among the outliers
+    st = _codec("rank", B, V, temp=1.0, token_cap=16)
+    st.set_messages(msgs)
+    toks = st.encode(fn, poll_every=2)
+    assert int((st.status & 3).sum().item()) == 0
+    for r in range(B):
+        want, hist, total = K.rank_encode(lambda t: base[r], K.bits_to_bytes_msb(msgs[r]))
+        assert toks[r] == [int(x) for x in want], r
+    st.set_tokens(toks, total_bits=[len(m) for m in msgs])
+    assert [b[:len(m)] for b, m in zip(st.decode(fn), msgs)] == msgs
