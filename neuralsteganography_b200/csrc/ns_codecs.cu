@@ -168,24 +168,8 @@ __device__ float* stage_row_bulk(const ns_codec_params& P, int row, CodecShared&
   return keys;
 }
 
-// The element whose 0-based position in the coder's order is `pos`, by a count histogram over
-// 2048 monotone key buckets + exact resolution inside the bucket.  Returns -1 if pos is out of range.
-__device__ int element_from_hist(const float* keys, int V, u64 pmax, u64 pmin, u64 pos, CodecShared& sm, int32_t* status);
-__device__ int element_at(const float* keys, int V, u64 pmax, u64 pmin, u64 pos, CodecShared& sm,
-                          int32_t* status) {
-  constexpr int NB = HIST_BYTES / 4;
-  const int tid = threadIdx.x;
-  const float m = key_of_pack(pmax);
-  const float span = m - key_of_pack(pmin);
-  const float scale = span > 0.0f ? (float)NB / span : 0.0f;
-  __syncthreads();
-  for (int i = tid; i < NB; i += NT) sm.hist[i] = 0;
-  if (tid == 0) sm.sc->list_count = 0;
-  __syncthreads();
-  for (int i = tid; i < V; i += NT) atomicAdd(&sm.hist[bin_of(keys[i], m, scale, NB)], 1u);
-  return element_from_hist(keys, V, pmax, pmin, pos, sm, status);
-}
-// the same with the count histogram (and list_count == 0) already in place
+// The element whose 0-based position in the coder's order is `pos`, from a count histogram over 2048 monotone key
+// buckets that the caller has filled (list_count == 0) + exact resolution inside the bucket.  Returns -1 if pos is out of range.
 __device__ int element_from_hist(const float* keys, int V, u64 pmax, u64 pmin, u64 pos, CodecShared& sm,
                                  int32_t* status) {
   constexpr int NB = HIST_BYTES / 4;

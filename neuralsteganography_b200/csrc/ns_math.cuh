@@ -55,7 +55,6 @@ NS_HD double ns_exp64_core(double a, const double* __restrict__ tab) {
   double r = ns_fma(nd, -NS_LN2_512_HI, a);
   r = ns_fma(nd, -NS_LN2_512_LO, r);
   double T = tab[n & (NS_EXP_N - 1)];
-  int32_t k = n >> NS_EXP_L;                         // arithmetic shift = floor
   double q = ns_fma(r, 1.0 / 24.0, 1.0 / 6.0);
   q = ns_fma(q, r, 0.5);
   double r2 = r * r;
@@ -63,10 +62,10 @@ NS_HD double ns_exp64_core(double a, const double* __restrict__ tab) {
   double e = ns_fma(T, p, T);
   // scale by 2^k through the exponent field (result stays normal for a >= -708)
 #if defined(__CUDA_ARCH__)
-  (void)k;
-  const int hi = __double2hiint(e) + ((n & ~(NS_EXP_N - 1)) << (20 - NS_EXP_L));   // high word += k << 20
+  const int hi = __double2hiint(e) + ((n & ~(NS_EXP_N - 1)) << (20 - NS_EXP_L));   // high word += k << 20, k = n >> 9
   return __hiloint2double(hi, __double2loint(e));
 #else
+  const int32_t k = n >> NS_EXP_L;                   // arithmetic shift = floor
   uint64_t bits = ns_double_as_u64(e) + ((uint64_t)(int64_t)k << 52);
   return ns_u64_as_double(bits);
 #endif
