@@ -49,6 +49,8 @@ extern "C" {
                                  multi-pass kernel (top-k inside the cutoff set, estimate outside
                                  its guard band, list overflow); results are identical */
 #define NS_ST_TOKEN_OVERFLOW 8 /* encode: token buffer full (ntok >= token_cap); stream stopped */
+#define NS_ST_RANK_DEFER 16   /* informational: the sweep kernel of the rank form (rank_ws given) left this row to the
+                                 row-resident kernel (not certainly top-k bound, finish_sent tail); results are identical */
 
 /* Arithmetic coder (A): code_base/arithmetic.py:78-217 (encode), :220-373 (decode). */
 typedef struct ns_ac_params {
@@ -111,12 +113,17 @@ typedef struct ns_ac_params {
      log p(selected token), KL(q_hat || p) in bits, entropy of the tempered distribution in bits.
      Requesting them routes the step through the exact kernel. */
   double* stats;
-  /* Reserved (a former streaming variant kept its scratch rows here); must be NULL / 0. */
-  void* scratch;
+  /* Optional second work queue, B+2 int32 zeroed once by the caller (same layout as slow_ws).  When given, a step whose
+     top-k binds (2 <= topk <= 512 < V, V >= 4096) starts with the sweep kernel of the rank form (csrc/ns_topk.cuh: no
+     resident row, two rows per SM); rows it does not carry are queued here and done by the row-resident kernel.
+     NULL = row-resident kernel for every row.  Results are identical. */
+  int32_t* rank_ws;
+  /* Reserved; must be 0. */
   int64_t scratch_stride;
   int32_t scratch_slots;
   /* Kernel choice for the throughput path: 0 = default (threshold form of the cutoff: the lean single-row kernel
-     ns_lean.cuh; rank form, topk <= 512: ns_fast.cuh), 2 = always ns_fast.cuh.  Results are identical. */
+     ns_lean.cuh; rank form, topk <= 512: ns_topk.cuh when rank_ws is given, then ns_fast.cuh), 2 = always ns_fast.cuh.
+     Results are identical. */
   int32_t variant;
 } ns_ac_params;
 
@@ -126,7 +133,6 @@ const char* ns_last_error_string(void);
 int ns_sizeof_ac_params(void);
 /* largest V the arithmetic-coder kernels accept on this build (the row lives in shared memory) */
 int ns_ac_max_vocab(void);
-/* largest V the two-row kernel accepts (it needs a second scratch set beside the shared-memory row) */
 
 /* one encode step for B streams (code_base/arithmetic.py:114-210 loop body) */
 int ns_ac_encode_step(const ns_ac_params* p, void* cuda_stream);

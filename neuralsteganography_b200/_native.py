@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("NS_CODER_LIB") or os.path.join(_PKG_DIR, "libns_coder
 
 NS_OK = 0
 PHASE_CODING, PHASE_TAIL, PHASE_DONE = 0, 1, 2
-ST_OUT_OF_RANGE, ST_BIN_OVERFLOW, ST_EST_RETRY, ST_TOKEN_OVERFLOW = 1, 2, 4, 8
+ST_OUT_OF_RANGE, ST_BIN_OVERFLOW, ST_EST_RETRY, ST_TOKEN_OVERFLOW, ST_RANK_DEFER = 1, 2, 4, 8, 16
 
 EXPORTS = (
     "ns_version", "ns_last_error_string", "ns_ac_max_vocab",
@@ -48,7 +48,7 @@ class AcParams(C.Structure):
         ("out_bits", C.c_void_p), ("out_stride", C.c_int64), ("out_len", C.c_void_p),
         ("nbits_out", C.c_void_p), ("trace", C.c_void_p),
         ("slow_ws", C.c_void_p), ("force_exact", C.c_int32), ("prof", C.c_void_p), ("stats", C.c_void_p),
-        ("scratch", C.c_void_p), ("scratch_stride", C.c_int64), ("scratch_slots", C.c_int32), ("variant", C.c_int32),
+        ("rank_ws", C.c_void_p), ("scratch_stride", C.c_int64), ("scratch_slots", C.c_int32), ("variant", C.c_int32),
     ]
 
 

@@ -89,6 +89,7 @@ class ArithmeticStreams:
         self.sent_end = sent_end
         self.force_exact = bool(force_exact)
         self.slow_ws = torch.zeros(self.B + 2, dtype=torch.int32, device=d)
+        self.rank_ws = torch.zeros(self.B + 2, dtype=torch.int32, device=d)   # work list sweep kernel -> row-resident kernel
         # kernel choice of the throughput path: 0 = default (two rows in flight per SM for the threshold form of the
         # cutoff), 2 = always the single-row kernel (NS_AC_VARIANT overrides; results are identical)
         import os as _os
@@ -181,7 +182,7 @@ class ArithmeticStreams:
         p.force_exact = int(self.force_exact)
         p.prof = N.ptr(getattr(self, "prof", None))
         p.stats = N.ptr(getattr(self, "stats", None))
-        p.scratch = None; p.scratch_stride = 0; p.scratch_slots = 0; p.variant = self.variant
+        p.rank_ws = self.rank_ws.data_ptr(); p.scratch_stride = 0; p.scratch_slots = 0; p.variant = self.variant
         return p
 
     def encode_step(self, logits: torch.Tensor) -> None:

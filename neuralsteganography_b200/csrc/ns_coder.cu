@@ -462,6 +462,10 @@ namespace nsf_smem {
 #undef NSF_FT
 #undef NSF_MIN_CTAS
 }  // namespace nsf_smem
+// rank form of the cutoff without a resident row: one 512-thread CTA per row, two per SM
+namespace nst {
+#include "ns_topk.cuh"
+}  // namespace nst
 // lean threshold-form kernel: one 1024-thread CTA per SM, one tight loop per sweep
 namespace nsl {
 #include "ns_lean.cuh"
@@ -530,9 +534,17 @@ int launch_exact(const ns_ac_params* p, u64* dbg_q, u64* dbg_meta, int32_t* slow
   return check_launch();
 }
 
-// fast kernel: persistent, one CTA per SM
+// rank form without a resident row: one CTA per row; rows it does not carry land in p->rank_ws
+template <bool UNIT, int MODE>
+int launch_topk(const ns_ac_params* p, cudaStream_t st) {
+  if (p->B == 0) return NS_OK;
+  nst::ac_topk_stream_kernel<UNIT, MODE><<<p->B, nst::KT, 0, st>>>(*p, p->rank_ws);
+  return check_launch();
+}
+
+// fast kernel: persistent, one CTA per SM; `rows` = work list (p->rank_ws) or nullptr for all rows
 template <bool UNIT, int MODE, bool RANK>
-int launch_fast(const ns_ac_params* p, cudaStream_t st) {
+int launch_fast(const ns_ac_params* p, cudaStream_t st, int32_t* rows = nullptr) {
   const int smem = FIXED_BYTES + (p->V + 8) * 4;
   static bool configured = false;
   int rc = configure(nsf_smem::ac_fast_kernel<UNIT, MODE, RANK>, &configured);
@@ -540,7 +552,7 @@ int launch_fast(const ns_ac_params* p, cudaStream_t st) {
   if (p->B == 0) return NS_OK;
   const int sms = num_sms();
   const int grid = p->B < sms ? p->B : sms;
-  nsf_smem::ac_fast_kernel<UNIT, MODE, RANK><<<grid, nsf_smem::FT, smem, st>>>(*p, p->slow_ws);
+  nsf_smem::ac_fast_kernel<UNIT, MODE, RANK><<<grid, nsf_smem::FT, smem, st>>>(*p, p->slow_ws, rows);
   return check_launch();
 }
 
@@ -573,7 +585,15 @@ int dispatch(const ns_ac_params* p, u64* dbg_q, u64* dbg_meta, void* stream) {
   constexpr int M2 = MODE == MODE_DEBUG ? MODE_ENC : MODE;
   const bool rank = p->topk >= 2 && p->topk < p->V && p->topk <= nsf_smem::F_K_CAP;
   const bool lean = !rank && p->variant == 0 && p->V >= nsl::L_MIN_VOCAB && p->V <= nsl::L_MAX_VOCAB;
-  if (rank) rc = (p->temp == 1.0) ? launch_fast<true, M2, true>(p, st) : launch_fast<false, M2, true>(p, st);
+  // rank form: the sweep kernel first (when the caller gave it a work list), then the row-resident kernel on the rows
+  // that one queued (not certainly in rank form, finish_sent tails, degenerate rows)
+  const bool topk_sweep = rank && p->variant == 0 && p->rank_ws != nullptr && p->V >= nst::K_MIN_VOCAB && p->topk <= nst::K_TOPK_CAP;
+  if (topk_sweep) {
+    rc = (p->temp == 1.0) ? launch_topk<true, M2>(p, st) : launch_topk<false, M2>(p, st);
+    if (rc != NS_OK) return rc;
+    rc = (p->temp == 1.0) ? launch_fast<true, M2, true>(p, st, p->rank_ws) : launch_fast<false, M2, true>(p, st, p->rank_ws);
+  }
+  else if (rank) rc = (p->temp == 1.0) ? launch_fast<true, M2, true>(p, st) : launch_fast<false, M2, true>(p, st);
   else if (lean) rc = (p->temp == 1.0) ? launch_lean<true, M2>(p, st) : launch_lean<false, M2>(p, st);
   else rc = (p->temp == 1.0) ? launch_fast<true, M2, false>(p, st) : launch_fast<false, M2, false>(p, st);
   if (rc != NS_OK) return rc;

@@ -308,7 +308,7 @@ static_assert(F_K_CAP <= FT && F_K_CAP <= 2 * F_C_CAP && F_RB_CAP <= F_BAND_CAP,
 static_assert(F_K_CAP * 16 <= F_NB * 4, "sorted arrays live in the histogram area");
 
 template <bool UNIT_TEMP, int MODE>
-__device__ __noinline__ int fast_rank_row(const ns_ac_params& P, int32_t* slow_ws, const int row,
+__device__ __noinline__ int fast_rank_row(const ns_ac_params& P, int32_t* slow_ws, const int row, const int nrow,
                                           const u64 m_lo, const u64 m_hi, const u64 m_window, const int m_slot,
                                           const int m_cursor, const int m_mlen, const int m_tok,
                                           uint32_t* hist, FScal* sc, CandEntry* top, BandEntry* bnd, const float* words,
@@ -464,8 +464,7 @@ __device__ __noinline__ int fast_rank_row(const ns_ac_params& P, int32_t* slow_w
   }
   __syncthreads();
   {   // the shared-memory row is not read again: the next row's bulk copy starts now, behind the rest of this row
-    const int nrow = row + (int)gridDim.x;
-    if (tid == 0 && nrow < P.B) f_issue_row(P, nrow, sc->bar, const_cast<float*>(words), &sc->issued_row);
+    if (tid == 0 && nrow >= 0) f_issue_row(P, nrow, sc->bar, const_cast<float*>(words), &sc->issued_row);
   }
   {
     uint32_t excl, total2;
@@ -600,7 +599,7 @@ __device__ __noinline__ int fast_rank_row(const ns_ac_params& P, int32_t* slow_w
 }
 
 template <bool UNIT_TEMP, int MODE, bool RANK>
-__device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws, const int row, const RowMeta meta,
+__device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws, const int row, const int nrow, const RowMeta meta,
                                          const FastSmem sm, uint32_t& parity, PhaseClock& pc) {
   double* tab = sm.tab; uint32_t* hist = sm.hist; BandEntry* band = sm.band; int* ulist = sm.ulist;
   CandEntry* clist = sm.clist; FScal* sc = sm.sc; float* words = sm.words;
@@ -623,8 +622,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
   // Called by every thread right after a CTA barrier that follows the row's last access to the shared-memory
   // row: thread 0 starts the next row's bulk copy, whose latency then overlaps the rest of this row.
   auto next_row_copy = [&]() {
-    const int nrow = row + (int)gridDim.x;
-    if (tid == 0 && nrow < P.B) f_issue_row(P, nrow, sc->bar, words, &sc->issued_row);
+    if (tid == 0 && nrow >= 0) f_issue_row(P, nrow, sc->bar, words, &sc->issued_row);
   };
   int phase = meta.phase;
   // a row that is skipped still has to consume its bulk copy if the previous row already started it
@@ -676,10 +674,9 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     auto raw4_p = [&](int c) -> float4 { return w4[c]; };    // masks are written into the shared row after L
     for (int i = tid; i < F_NB / 4; i += FT) reinterpret_cast<uint4*>(hist)[i] = make_uint4(0, 0, 0, 0);
     {   // prefetch this CTA's next row into L2 while this one is processed
-      const int nrow = row + gridDim.x;
       // one bulk prefetch per warp leader: the copy engine walks the lines.  Per-lane prefetch instructions
       // (32 lines each) occupy the load/store pipe for ~1.5k cycles and hold back the estimate's shared loads.
-      if (nrow < P.B && (tid & 31) == 0) {
+      if (nrow >= 0 && (tid & 31) == 0) {
         const char* np = reinterpret_cast<const char*>(P.logits + (size_t)nrow * (size_t)P.ld);
         const char* a0 = reinterpret_cast<const char*>(((uintptr_t)np + 15u) & ~(uintptr_t)15u);
         const int nbytes = (int)(np + (size_t)V * 4 - a0) & ~15;
@@ -932,7 +929,7 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
     if (RANK && P.topk < V && P.topk >= 2 && P.topk <= F_K_CAP) {
       // top-k binds if more than topk tokens are above the cutoff even should the estimate be 2% off
       const float kappa_r = kappa_hi + 0.02f * (float)temp;
-      if (fast_rank_row<UNIT_TEMP, MODE>(P, slow_ws, row, meta.lo, meta.hi, meta.window, meta.slot, meta.cursor, meta.mlen,
+      if (fast_rank_row<UNIT_TEMP, MODE>(P, slow_ws, row, nrow, meta.lo, meta.hi, meta.window, meta.slot, meta.cursor, meta.mlen,
                                         meta.tok, hist, sc, clist, band, words, tab, mis, W4, M, top_id, kappa_r, clamp_key, dm)) {
         pc.mark(7);
         return;
@@ -1428,45 +1425,59 @@ __device__ __forceinline__ void fast_row(const ns_ac_params& P, int32_t* slow_ws
 }
 
 // RANK: compiled with the rank-form path (host picks it when 2 <= topk <= F_K_CAP and topk < V); the other
-// instantiation is the pure threshold-form kernel
+// instantiation is the pure threshold-form kernel.  `rows` = nullptr: all P.B rows; else a work list {count, done,
+// rows...} (the rows ns_topk.cuh did not carry): the CTAs walk the list and the last one to finish empties it.
 template <bool UNIT_TEMP, int MODE, bool RANK = false>
-__global__ void __launch_bounds__(FT, NSF_MIN_CTAS) ac_fast_kernel(const __grid_constant__ ns_ac_params P, int32_t* slow_ws) {
+__global__ void __launch_bounds__(FT, NSF_MIN_CTAS) ac_fast_kernel(const __grid_constant__ ns_ac_params P, int32_t* slow_ws, int32_t* rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  FastSmem sm;
-  sm.tab = reinterpret_cast<double*>(smem_raw);
-  sm.hist = reinterpret_cast<uint32_t*>(smem_raw + NS_EXP_N * 8);
-  sm.band = reinterpret_cast<BandEntry*>(smem_raw + NS_EXP_N * 8 + F_NB * 4);
-  sm.ulist = reinterpret_cast<int*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16);
-  sm.clist = reinterpret_cast<CandEntry*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16 + F_U_CAP * 4);
-  sm.sc = reinterpret_cast<FScal*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16 + F_U_CAP * 4 + 2 * F_C_CAP * 16);
-  sm.words = reinterpret_cast<float*>(smem_raw + FIXED_BYTES);   // element id lives at words[id + mis]
   const int tid = threadIdx.x;
-  constexpr int HELPER = FT - 32;                          // lane that fetches the next row's scalars
-  for (int i = tid; i < NS_EXP_N; i += FT) sm.tab[i] = c_exp_tab[i];
-  if (tid == 0) {
-    for (int k = 0; k < F_PIECES; ++k) f_mbar_init(&sm.sc->bar[k], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    sm.sc->issued_row = -1;
+  const int n_rows = rows ? rows[0] : P.B;
+  if (n_rows > 0) {
+    FastSmem sm;
+    sm.tab = reinterpret_cast<double*>(smem_raw);
+    sm.hist = reinterpret_cast<uint32_t*>(smem_raw + NS_EXP_N * 8);
+    sm.band = reinterpret_cast<BandEntry*>(smem_raw + NS_EXP_N * 8 + F_NB * 4);
+    sm.ulist = reinterpret_cast<int*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16);
+    sm.clist = reinterpret_cast<CandEntry*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16 + F_U_CAP * 4);
+    sm.sc = reinterpret_cast<FScal*>(smem_raw + NS_EXP_N * 8 + F_NB * 4 + F_BAND_CAP * 16 + F_U_CAP * 4 + 2 * F_C_CAP * 16);
+    sm.words = reinterpret_cast<float*>(smem_raw + FIXED_BYTES);   // element id lives at words[id + mis]
+    constexpr int HELPER = FT - 32;                          // lane that fetches the next row's scalars
+    auto row_at = [&](int i) -> int { return rows ? rows[2 + i] : i; };
+    for (int i = tid; i < NS_EXP_N; i += FT) sm.tab[i] = c_exp_tab[i];
+    if (tid == 0) {
+      for (int k = 0; k < F_PIECES; ++k) f_mbar_init(&sm.sc->bar[k], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      sm.sc->issued_row = -1;
+    }
+    if (tid == HELPER && (int)blockIdx.x < n_rows) sm.sc->meta[0] = f_load_meta(P, row_at(blockIdx.x), MODE);
+    uint32_t parity = 0;                                     // bit k: phase parity of piece k's mbarrier
+    PhaseClock pc;
+    pc.on = (P.prof != nullptr) && tid == 0;
+    pc.last = 0;
+    for (int k = 0; k < 16; ++k) pc.acc[k] = 0;
+    int it = 0;
+    for (int i = blockIdx.x; i < n_rows; i += gridDim.x, ++it) {
+      pc.start();
+      __syncthreads();                                       // previous row is finished with shared memory
+      pc.mark(10);                                           // waiting for the previous row's stragglers
+      const RowMeta meta = sm.sc->meta[it & 1];
+      RowMeta next;
+      const int row = row_at(i);
+      const int nrow = i + (int)gridDim.x < n_rows ? row_at(i + (int)gridDim.x) : -1;
+      const bool fetch = (tid == HELPER) && (nrow >= 0);
+      if (fetch) next = f_load_meta(P, nrow, MODE);          // loads in flight while the row is processed
+      fast_row<UNIT_TEMP, MODE, RANK>(P, slow_ws, row, nrow, meta, sm, parity, pc);
+      if (fetch) sm.sc->meta[(it + 1) & 1] = next;
+      if (pc.on) pc.acc[15] += 1;
+    }
+    if (pc.on) for (int k = 0; k < 16; ++k) atomicAdd((unsigned long long*)&P.prof[k], (unsigned long long)pc.acc[k]);
   }
-  if (tid == HELPER && (int)blockIdx.x < P.B) sm.sc->meta[0] = f_load_meta(P, blockIdx.x, MODE);
-  uint32_t parity = 0;                                     // bit k: phase parity of piece k's mbarrier
-  PhaseClock pc;
-  pc.on = (P.prof != nullptr) && tid == 0;
-  pc.last = 0;
-  for (int k = 0; k < 16; ++k) pc.acc[k] = 0;
-  int it = 0;
-  for (int row = blockIdx.x; row < P.B; row += gridDim.x, ++it) {
-    pc.start();
-    __syncthreads();                                       // previous row is finished with shared memory
-    pc.mark(10);                                           // waiting for the previous row's stragglers
-    const RowMeta meta = sm.sc->meta[it & 1];
-    RowMeta next;
-    const int nrow = row + gridDim.x;
-    const bool fetch = (tid == HELPER) && (nrow < P.B);
-    if (fetch) next = f_load_meta(P, nrow, MODE);          // loads in flight while the row is processed
-    fast_row<UNIT_TEMP, MODE, RANK>(P, slow_ws, row, meta, sm, parity, pc);
-    if (fetch) sm.sc->meta[(it + 1) & 1] = next;
-    if (pc.on) pc.acc[15] += 1;
+  if (rows) {                                                // every CTA has read the count before the last one clears it
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      const int d = atomicAdd(&rows[1], 1);
+      if (d == (int)gridDim.x - 1) { rows[0] = 0; rows[1] = 0; __threadfence(); }
+    }
   }
-  if (pc.on) for (int k = 0; k < 16; ++k) atomicAdd((unsigned long long*)&P.prof[k], (unsigned long long)pc.acc[k]);
 }

@@ -256,9 +256,11 @@ def test_device_statistics_match_oracle():
     (50257, 26, 64, 1.0, 3.0, 0.25),      # quantised logits: many exact ties across the top-k boundary
     (5000, 20, 100, 1.0, 2.0, 0.5),       # small vocabulary, dense ties (boundary bucket overflow -> hand-over)
 ])
-def test_rank_form_fast_path_matches_exact_kernel(V, precision, topk, temp, scale, quant):
-    """The top-k-binding path of the throughput kernel against the exact kernel, encode and decode: same
-    tokens, intervals, cursors, recovered bits; plus the oracle on a few streams."""
+@pytest.mark.parametrize("variant", [0, 2])
+def test_rank_form_fast_path_matches_exact_kernel(V, precision, topk, temp, scale, quant, variant):
+    """The top-k-binding paths of the throughput kernels (variant 0: the sweep kernel ns_topk.cuh + the row-resident
+    kernel on what it leaves; variant 2: the row-resident kernel alone) against the exact kernel, encode and decode:
+    same tokens, intervals, cursors, recovered bits; plus the oracle on a few streams."""
     B, T, steps = 48, 4, 20
     g = torch.Generator(device="cuda").manual_seed(1000 + topk)
     pool = [torch.randn(B, V, generator=g, device="cuda") * scale for _ in range(T)]
@@ -268,7 +270,8 @@ def test_rank_form_fast_path_matches_exact_kernel(V, precision, topk, temp, scal
     msgs = [message_bits(1500 + r, 256).tolist() for r in range(B)]
     enc = {}
     for force in (False, True):
-        st = _streams(B, V, precision=precision, temp=temp, topk=topk, token_cap=steps + 2, trace=True, force_exact=force)
+        st = _streams(B, V, precision=precision, temp=temp, topk=topk, token_cap=steps + 2, trace=True, force_exact=force,
+                      variant=variant)
         st.set_messages(msgs)
         st.encode(fn, poll_every=64, max_steps=steps)
         enc[force] = st
@@ -279,10 +282,15 @@ def test_rank_form_fast_path_matches_exact_kernel(V, precision, topk, temp, scal
     if (topk, quant, scale) == (300, 0.0, 3.0):
         # config 2's settings on ordinary rows: the rank-form path of the throughput kernel codes every row itself
         assert int(((a.status & 4) != 0).sum().item()) == 0
+        # ... and with variant 0 the sweep kernel does, leaving nothing to the row-resident one
+        assert int(((a.status & 16) != 0).sum().item()) == 0
+    if variant == 2:
+        assert int(((a.status & 16) != 0).sum().item()) == 0
+    assert int(a.rank_ws[:2].abs().sum().item()) == 0          # the work list is empty again after every step
     toks = a.token_lists()
     dec = {}
     for force in (False, True):
-        st = _streams(B, V, precision=precision, temp=temp, topk=topk, token_cap=steps + 2, force_exact=force)
+        st = _streams(B, V, precision=precision, temp=temp, topk=topk, token_cap=steps + 2, force_exact=force, variant=variant)
         st.set_tokens(toks)
         dec[force] = st.decode(fn)
     assert dec[False] == dec[True]
@@ -311,3 +319,31 @@ def test_rank_form_decode_of_foreign_token():
     for x, y in zip(*outs):
         assert torch.equal(x, y)
     assert bool((outs[0][4] == 1).all().item())
+
+
+def test_sweep_kernel_tail_and_masks_match_exact_kernel():
+    """finish_sent tails and forbidden tokens through the rank form's sweep kernel (variant 0): the forbidden ids carry
+    the largest logits of every row (they must get probability 0), short messages put the streams into the tail after
+    a few tokens (those rows are left to the row-resident kernel)."""
+    V, B, steps = 50257, 16, 14
+    g = torch.Generator(device="cuda").manual_seed(99)
+    pool = [torch.randn(B, V, generator=g, device="cuda") * 3.0 for _ in range(3)]
+    for p in pool:
+        p[:, V - 1] = 40.0
+        p[:, 628] = 35.0
+    sent_end = (torch.rand(V, generator=g, device="cuda") < 0.3).to(torch.uint8)
+    msgs = [message_bits(300 + r, 30 + r).tolist() for r in range(B)]
+    out = {}
+    for force in (False, True):
+        st = _streams(B, V, precision=26, temp=0.9, topk=300, token_cap=steps + 2, finish_sent=True, sent_end=sent_end,
+                      force_exact=force, variant=0)
+        st.set_messages(msgs)
+        st.encode(lambda t: pool[t % 3], poll_every=64, max_steps=steps)
+        out[force] = st
+    a, b = out[False], out[True]
+    for name in ("tokens", "lo", "hi", "cursor", "ntok", "phase"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert int((a.status & 3).sum().item()) == 0
+    assert bool(((a.status & 16) != 0).any().item())            # the tails went through the work list
+    assert not bool((a.tokens == V - 1).any().item()) and not bool((a.tokens == 628).any().item())
+    assert int(a.rank_ws[:2].abs().sum().item()) == 0
