@@ -1,43 +1,59 @@
 // ns_topk.cuh -- arithmetic-coder step, rank form of the cutoff (code_base/arithmetic.py:75 with top-k binding),
 // WITHOUT a resident row (sm_100a).  Included by ns_coder.cu inside namespace nst, after the shared definitions.
 //
-// When more than topk tokens have p >= 1/range the kept set is the topk largest logits (arithmetic.py:142) and
-// nothing below them matters: no fp64 work on the row at all.  The row-resident kernel (ns_fast.cuh,
-// fast_rank_row) spends its time in a chain of ~25 barrier-separated steps on one row per SM (issue slots 36 %
-// busy).  Here the row is swept from global memory like the rank codec does (ns_codecs_stream.cuh): one
-// 512-thread CTA per row, 25 KB of shared memory, two CTAs per SM, so the chain of one row hides under the
-// sweeps of another.
-//   sample   one chunk per thread: bucket range of the count histogram (any monotone bucket function gives
-//            the same kept set: the order inside a bucket is resolved exactly) and the reference of the estimate
-//   sweep 1  (HBM) row maximum, fp32 estimate of sum exp((x - M)/temp), count histogram of the keys
-//   scan     bucket holding position topk of the coder's order; the row is certainly in rank form when every
-//            key of the buckets up to that one lies above the estimated cutoff plus the 2 % guard
-//   sweep 2  (L2) the keys of those buckets, grouped by bucket at their prefix (count | prefix per bucket)
-//   chain    order inside each bucket (key, lower id first), exp64 of the topk kept tokens, bin widths,
-//            prefix sums, overfill, search (encode) / position of the observed token (decode), interval update
-//            -- the arithmetic of fast_rank_row, same reduction order, same integers
-// Rows this kernel does not carry (not certainly in rank form, estimate outside its guard, lists too small,
+// When at least topk tokens have p >= 1/range the kept set is the topk largest logits (arithmetic.py:142) and
+// nothing below them matters: no fp64 work on the row at all, and the row is read from HBM exactly ONCE with a
+// dozen instructions per 16-byte chunk.  One 512-thread CTA per row, 44 KB of shared memory, several CTAs per SM,
+// so the chain of one row hides under the sweeps of the others.
+//   sample   two chunks per thread (4096 logits, strided over the row): count histogram of the sample -> a key
+//            bound k_c that about 2.5 topk + 64 keys of the row exceed (order statistics of the sample: the
+//            count above the r-th largest sample key has relative spread 1/sqrt(r))
+//   sweep    (HBM, once) per chunk: its maximum m -> row maximum M, an UPPER bound 4 sum_chunks exp((m - M)/temp)
+//            of the softmax normaliser (one ex2 per chunk), and the chunk index to a hit list when m >= k_c
+//   gather   the hit chunks again (L2): the keys >= k_c, the candidates; at least topk of them means the topk
+//            largest keys of the row are the topk largest candidates (ties included: equal keys are candidates too)
+//   order    count histogram of the candidates over [k_c, M] -> grouped by bucket -> exact order inside each bucket
+//            (key, lower id first) -> rank of every candidate; the row is certainly in rank form when the key of rank
+//            topk-1 has p >= 1/range even against the upper bound of the normaliser (plus the guard band)
+//   chain    exp64 of the topk kept tokens, bin widths, prefix sums, overfill, search (encode) / position of the
+//            observed token (decode), interval update -- the arithmetic of fast_rank_row, same reduction order,
+//            same integers
+// Rows this kernel does not carry (not certainly in rank form, too few / too many candidates, degenerate ties,
 // finish_sent tail) are queued in `mid` = {count, done, rows...}; ac_fast_kernel then runs on that list.
 
 constexpr int KT = 512;                      // threads per CTA
 constexpr int KW = KT / 32;
 constexpr int K_NB = 2048;                   // histogram buckets
 constexpr int K_BPT = K_NB / KT;
-constexpr int K_CAP = 1024;                  // gathered keys (the topk kept ones + the rest of the boundary bucket)
-constexpr int K_TOPK_CAP = 512;              // one thread per kept token
-constexpr int K_MIN_VOCAB = 4096;
+constexpr int K_CAP = 1536;                  // candidates (keys >= k_c)
+constexpr int K_HCAP = 2048;                 // chunks holding a candidate
+constexpr int K_TOPK_CAP = 384;              // one thread per kept token; 2.5 topk + 64 stays well below K_CAP
+constexpr int K_MIN_VOCAB = 8192;            // the sample needs 1024 distinct interior chunks
+#ifndef NST_U
+#define NST_U 4
+#endif
+#ifndef NST_MIN_CTAS
+#define NST_MIN_CTAS 3
+#endif
+constexpr int K_U = NST_U;                   // chunk loads in flight per thread
+constexpr int K_MIN_CTAS = NST_MIN_CTAS;     // CTAs per SM the register budget is cut for
+constexpr int K_TIE_CAP = 256;               // keys in the boundary bucket (the order inside a bucket is quadratic)
 constexpr float K_MAGIC = 2097152.0f;        // 2^21: a float counts quarters there
 constexpr float K_BAND_EPS = 0.0009765625f;  // the guard band of the throughput kernels (F_BAND_EPS)
-template <int N> struct KDepth { static constexpr int value = N; };   // chunk loads in flight per thread of a sweep
 static_assert(K_TOPK_CAP <= KT && K_TOPK_CAP * 12 <= K_NB * 4 && K_TOPK_CAP * 8 <= K_CAP * 16, "chain arrays live in the histogram / list areas");
+static_assert(K_HCAP * 4 <= K_CAP * 16, "the hit list lives in the list area");
+static_assert(K_U >= 1 && K_U <= 8, "hit entries carry K_U mask bits under the chunk index");
+static_assert(5 * K_TOPK_CAP / 2 + 64 + 400 <= K_CAP, "room for the spread of the candidate count");
 
 struct KEntry { float key; int id; uint32_t ex; uint32_t pad; };   // ex = first list position of the entry's bucket
+struct KCand { float key; int id; };
 struct KScal {
   u64 red[KW];
   uint32_t wmax[KW], smax[KW], smin[KW];
   float wsum[KW];
-  int sel_bin, res_idx, res_found, pad;
+  int sel_bin, res_idx, res_found, nhit, ncand;
   uint32_t sel_prefix, sel_cnt;
+  float kth_key;
 };
 
 __device__ __forceinline__ float k_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -53,9 +69,10 @@ __device__ __forceinline__ void k_defer(const ns_ac_params& P, int32_t* mid, int
 }
 
 template <bool UNIT_TEMP, int MODE>
-__global__ void __launch_bounds__(KT, 2) ac_topk_stream_kernel(const __grid_constant__ ns_ac_params P, int32_t* mid) {
-  __shared__ __align__(16) uint32_t hist[K_NB];              // count histogram; later es[topk] (fp64) and sid[topk]
-  __shared__ __align__(16) KEntry list[K_CAP];               // gathered keys; later the prefix sums of the bin widths
+__global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __grid_constant__ ns_ac_params P, int32_t* mid) {
+  __shared__ __align__(16) uint32_t hist[K_NB];              // count histograms; later es[topk] (fp64) and sid[topk]
+  __shared__ __align__(16) KEntry list[K_CAP];               // hit chunks; candidates grouped by bucket; prefix sums of the bin widths
+  __shared__ __align__(16) KCand cand[K_CAP];                // candidates in arrival order
   __shared__ KScal sc;
   const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, V = P.V, K = P.topk;
   // ---- the stream's scalars
@@ -110,107 +127,20 @@ __global__ void __launch_bounds__(KT, 2) ac_topk_stream_kernel(const __grid_cons
     }
     return v;
   };
-  // interior chunks 1 .. W4-2 with U straight 128-bit loads in flight per thread, then the two edge chunks
-  // element-wise by two threads (-inf outside the row).  body(v, first id, edge)
-  auto sweep = [&](bool last, auto body, auto depth) {
-    constexpr int U = decltype(depth)::value;
-    int c = 1 + tid;
-    for (; c + (U - 1) * KT < W4 - 1; c += U * KT) {
-      float4 v[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) v[u] = ldg4(c + u * KT, last);
-#pragma unroll
-      for (int u = 0; u < U; ++u) body(fold(v[u], c + u * KT), 4 * (c + u * KT) - mis, false);
-    }
-    for (; c < W4 - 1; c += KT) body(fold(ldg4(c, last), c), 4 * c - mis, false);
-    if (tid == 0 || tid == 32) {
-      const int ce = tid ? W4 - 1 : 0, b0 = 4 * ce - mis;
-      float4 v;
-      v.x = (b0 >= 0 && b0 < V) ? g[b0] : -INFINITY;
-      v.y = (b0 + 1 >= 0 && b0 + 1 < V) ? g[b0 + 1] : -INFINITY;
-      v.z = (b0 + 2 >= 0 && b0 + 2 < V) ? g[b0 + 2] : -INFINITY;
-      v.w = (b0 + 3 >= 0 && b0 + 3 < V) ? g[b0 + 3] : -INFINITY;
-      body(fold(v, ce), b0, true);
-    }
+  // any chunk, the two edge chunks element-wise (-inf outside the row)
+  auto chunk = [&](int c, bool last) -> float4 {
+    if (c >= 1 && c < W4 - 1) return fold(ldg4(c, last), c);
+    const int b0 = 4 * c - mis;
+    float4 v;
+    v.x = (b0 >= 0 && b0 < V) ? g[b0] : -INFINITY;
+    v.y = (b0 + 1 >= 0 && b0 + 1 < V) ? g[b0 + 1] : -INFINITY;
+    v.z = (b0 + 2 >= 0 && b0 + 2 < V) ? g[b0 + 2] : -INFINITY;
+    v.w = (b0 + 3 >= 0 && b0 + 3 < V) ? g[b0 + 3] : -INFINITY;
+    return fold(v, c);
   };
-  for (int i = tid; i < K_NB; i += KT) hist[i] = 0;
-  // ---- sample: extent of one chunk per thread -> bucket range (widened: the sample misses the tails), reference
-  float scale, boff, ref;
-  {
-    float sb = -INFINITY, sl = INFINITY;
-    const int stride = (W4 - 2) / KT > 0 ? (W4 - 2) / KT : 1;
-    const int cs = 1 + tid * stride;
-    if (cs < W4 - 1) {
-      const float4 v = fold(ldg4(cs, false), cs);
-      sb = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
-      sl = fminf(fminf(v.x > -1e9f ? v.x : INFINITY, v.y > -1e9f ? v.y : INFINITY),
-                 fminf(v.z > -1e9f ? v.z : INFINITY, v.w > -1e9f ? v.w : INFINITY));
-    }
-    const uint32_t a = __reduce_max_sync(0xffffffffu, ns_f32_orderable(sb));
-    const uint32_t b = __reduce_min_sync(0xffffffffu, ns_f32_orderable(sl));
-    if (lane == 0) { sc.smax[warp] = a; sc.smin[warp] = b; }
-    __syncthreads();                                         // (also: the histogram is clear)
-    uint32_t ga = 0, gb = 0xffffffffu;
-#pragma unroll
-    for (int w = 0; w < KW; ++w) { ga = max(ga, sc.smax[w]); gb = min(gb, sc.smin[w]); }
-    float smax = key_of_pack((u64)ga << 32), smin = key_of_pack((u64)gb << 32);
-    if (!(smax > -3.0e38f) || !(smax < 3.0e38f) || !(smin > -3.0e38f) || !(smin < 3.0e38f)) { smax = 1.0f; smin = -1.0f; }
-    float span = smax - smin;
-    if (!(span > 0.0f)) span = 1.0f;
-    const float hi_p = smax + 0.25f * span, lo_p = smin - 0.25f * span;
-    scale = (float)K_NB / (hi_p - lo_p);
-    boff = hi_p * scale + K_MAGIC;
-    if (!(scale > 0.0f) || !(scale < 3.0e38f) || !(fabsf(boff) < 3.0e38f)) { scale = 0.0f; boff = K_MAGIC; }
-    ref = smax;
-  }
-  // ---- sweep 1 (HBM): maximum, estimate of the softmax normaliser against the fixed reference, count histogram
-  const float c2 = (float)(1.4426950408889634 / P.temp);     // log2(e)/temp
-  float bk = -INFINITY, ts0 = 0.f, ts1 = 0.f;
-  {
-    const float nrc = -ref * c2;
-    const uint32_t hb = (uint32_t)__cvta_generic_to_shared(hist);
-    sweep(false, [&](const float4 v, int id, bool edge) {
-      bk = fmaxf(bk, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
-      ts0 += k_ex2(fmaf(v.x, c2, nrc)); ts1 += k_ex2(fmaf(v.y, c2, nrc));
-      ts0 += k_ex2(fmaf(v.z, c2, nrc)); ts1 += k_ex2(fmaf(v.w, c2, nrc));
-      const float xs[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (edge && (unsigned)(id + j) >= (unsigned)V) continue;          // padding of the edge chunks is not a token
-        asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(hb + k_off(xs[j], scale, boff)), "r"(1u) : "memory");
-      }
-    }, KDepth<8>());
-  }
-  float M, ssum;
-  {
-    const uint32_t wk = __reduce_max_sync(0xffffffffu, ns_f32_orderable(bk + 0.0f));
-    float wts = ts0 + ts1;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wts += __shfl_xor_sync(0xffffffffu, wts, o);
-    if (lane == 0) { sc.wmax[warp] = wk; sc.wsum[warp] = wts; }
-    __syncthreads();                                         // (also: the histogram is complete)
-    uint32_t mk = 0;
-    float tot = 0.f;
-#pragma unroll
-    for (int w = 0; w < KW; ++w) { mk = max(mk, sc.wmax[w]); tot += sc.wsum[w]; }
-    M = key_of_pack((u64)mk << 32);
-    ssum = tot * k_ex2((ref - M) * c2);
-  }
-  // ---- row constants (every thread, same bits): the formulas of fast_row
-  const double thr = __ddiv_rn(1.0, (double)R);              // :141
-  const double Md = (double)M;
-  const double dm = UNIT_TEMP ? Md : __ddiv_rn(Md, P.temp);
-  const float tf = (float)P.temp;
-  const float key_th = fmaf(tf * 0.6931471805599453f, __log2f((float)(thr * (double)ssum)), M);   // p >= 1/R <=> key >= M + temp ln(sum / R)
-  const float kappa_lo = key_th - tf * K_BAND_EPS;
-  const float kappa_r = key_th + tf * K_BAND_EPS + 0.02f * tf;   // top-k binds even should the estimate be 2 % off
-  const float clamp_key = (float)(Md - 700.0 * P.temp);
-  if (!(ssum > 0.0f) || !(ssum < 3.0e38f) || !(R >= 2) || !(kappa_lo > clamp_key) || !(M > -3.0e38f) || !(M < 3.0e38f) || !(scale > 0.0f)) {
-    if (tid == 0) k_defer(P, mid, row);
-    return;
-  }
-  // ---- scan: bucket of position K (0-based: the first token NOT kept); buckets become count | prefix << 16
-  {
+  // exclusive scan of the histogram (bucket 0 = largest keys) and the bucket holding position `pos`; the buckets
+  // become count | prefix << 16 (pack) or zero
+  auto scan_find = [&](int pos, bool pack) {
     uint32_t hl[K_BPT], tsum = 0;
 #pragma unroll
     for (int b = 0; b < K_BPT; ++b) { hl[b] = hist[tid * K_BPT + b]; tsum += hl[b]; }
@@ -226,42 +156,169 @@ __global__ void __launch_bounds__(KT, 2) ac_topk_stream_kernel(const __grid_cons
 #pragma unroll
     for (int b = 0; b < K_BPT; ++b) {
       const uint32_t c = hl[b];
-      if (c != 0 && excl <= (uint32_t)K && (uint32_t)K < excl + c) { sc.sel_bin = tid * K_BPT + b; sc.sel_prefix = excl; sc.sel_cnt = c; }
-      hist[tid * K_BPT + b] = c | ((excl < 0xffffu ? excl : 0xffffu) << 16);
+      if (c != 0 && excl <= (uint32_t)pos && (uint32_t)pos < excl + c) { sc.sel_bin = tid * K_BPT + b; sc.sel_prefix = excl; sc.sel_cnt = c; }
+      hist[tid * K_BPT + b] = pack ? (c | (excl << 16)) : 0u;
       excl += c;
     }
     __syncthreads();
+  };
+  for (int i = tid; i < K_NB; i += KT) hist[i] = 0;
+  if (tid == 0) { sc.nhit = 0; sc.ncand = 0; sc.kth_key = -INFINITY; }
+  // ---- sample: two chunks per thread, strided over the row -> bucket range, reference of the bound, key bound k_c
+  float k_c, ref;
+  {
+    const int NI = W4 - 2;                                   // interior chunks 1 .. W4-2 (>= 2 KT: K_MIN_VOCAB)
+    const int cs0 = 1 + (int)(((long long)tid * NI) >> 10), cs1 = 1 + (int)(((long long)(tid + KT) * NI) >> 10);
+    const float4 a = fold(ldg4(cs0, false), cs0), b = fold(ldg4(cs1, false), cs1);
+    const float xs[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float sb = -INFINITY, sl = INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sb = fmaxf(sb, xs[j]); sl = fminf(sl, xs[j] > -1e9f ? xs[j] : INFINITY); }
+    const uint32_t ra = __reduce_max_sync(0xffffffffu, ns_f32_orderable(sb));
+    const uint32_t rb = __reduce_min_sync(0xffffffffu, ns_f32_orderable(sl));
+    if (lane == 0) { sc.smax[warp] = ra; sc.smin[warp] = rb; }
+    __syncthreads();                                         // (also: the histogram is clear)
+    uint32_t ga = 0, gb = 0xffffffffu;
+#pragma unroll
+    for (int w = 0; w < KW; ++w) { ga = max(ga, sc.smax[w]); gb = min(gb, sc.smin[w]); }
+    float smax = key_of_pack((u64)ga << 32), smin = key_of_pack((u64)gb << 32);
+    if (!(smax > -3.0e38f) || !(smax < 3.0e38f) || !(smin > -3.0e38f) || !(smin < 3.0e38f)) { smax = 1.0f; smin = -1.0f; }
+    float span = smax - smin;
+    if (!(span > 0.0f)) span = 1.0f;
+    const float hi_p = smax + 0.001f * span, lo_p = smin - 0.001f * span;
+    float scale = (float)K_NB / (hi_p - lo_p);
+    float boff = hi_p * scale + K_MAGIC;
+    if (!(scale > 0.0f) || !(scale < 3.0e38f) || !(fabsf(boff) < 3.0e38f)) { scale = 0.0f; boff = K_MAGIC; }
+    ref = smax;
+    const uint32_t hb = (uint32_t)__cvta_generic_to_shared(hist);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(hb + k_off(xs[j], scale, boff)), "r"(1u) : "memory");
+    __syncthreads();
+    // sample rank whose key about 2.5 K + 64 keys of the row exceed (the sample holds 8 KT of the V logits)
+    const int want = (5 * K) / 2 + 64;
+    const int rs = (int)(((long long)want * (8 * KT) + V - 1) / V);
+    scan_find(rs - 1, false);                                // (leaves the histogram clear)
+    const int tb = sc.sel_bin;
+    // every key of bucket b satisfies (hi_p - k) scale < b + 7/8; one more bucket absorbs the rounding of the offset
+    k_c = hi_p - ((float)tb + 2.0f) / scale;
+    if (tb < 0 || !(scale > 0.0f) || !(k_c > -3.0e38f) || !(k_c < 3.0e38f)) {
+      if (tid == 0) k_defer(P, mid, row);
+      return;
+    }
   }
-  const int tb = sc.sel_bin;
-  const int total = (int)(sc.sel_prefix + sc.sel_cnt);       // keys in the buckets 0 .. tb: at least K + 1
-  // every key of bucket b satisfies (hi_p - k) scale < b + 7/8; one more bucket absorbs the rounding of the offset
-  const float hi_p = (boff - K_MAGIC) / scale;
-  const float key_lb = hi_p - ((float)tb + 2.0f) / scale;
-  const float key_gather = hi_p - ((float)tb + 3.0f) / scale;   // chunk test of the gather: below every key of bucket tb
-  if (tb < 0 || tb >= K_NB - 1 || total > K_CAP || !(key_lb >= kappa_r)) {   // not certainly in rank form / too many ties
+  // ---- the sweep (HBM, once): chunk maxima -> row maximum, upper bound of the normaliser, hit list
+  const float c2 = (float)(1.4426950408889634 / P.temp);     // log2(e)/temp
+  float bk = -INFINITY, ts0 = 0.f, ts1 = 0.f;
+  int* hits = reinterpret_cast<int*>(list);                  // [K_HCAP]
+  {
+    const float nrc = -ref * c2;
+    auto one = [&](const float4 v, float& ts) -> bool {
+      const float m = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+      bk = fmaxf(bk, m);
+      ts += k_ex2(fmaf(m, c2, nrc));
+      return m >= k_c;
+    };
+    // hit list entry: first chunk << K_U | mask of the thread's chunks c + u KT holding a candidate
+    auto push = [&](int c, uint32_t hm) {
+      const int p = atomicAdd(&sc.nhit, 1);
+      if (p < K_HCAP) hits[p] = (int)(((uint32_t)c << K_U) | hm);
+    };
+    // interior chunk c belongs to thread (c - 1) mod KT; the (at most two) chunks with a forbidden id are folded by
+    // their owner in the iteration that holds them -- one range test per K_U chunks
+    const int own0 = (mc0 >= 1 && mc0 < W4 - 1 && ((mc0 - 1) & (KT - 1)) == tid) ? mc0 : -(1 << 30);
+    const int own1 = (mc1 >= 1 && mc1 < W4 - 1 && ((mc1 - 1) & (KT - 1)) == tid) ? mc1 : -(1 << 30);
+    int c = 1 + tid;
+    for (; c + (K_U - 1) * KT < W4 - 1; c += K_U * KT) {
+      float4 v[K_U];
+#pragma unroll
+      for (int u = 0; u < K_U; ++u) v[u] = ldg4(c + u * KT, true);
+      if ((unsigned)(own0 - c) < (unsigned)(K_U * KT) || (unsigned)(own1 - c) < (unsigned)(K_U * KT)) {
+#pragma unroll
+        for (int u = 0; u < K_U; ++u) v[u] = fold(v[u], c + u * KT);
+      }
+      uint32_t hm = 0;
+#pragma unroll
+      for (int u = 0; u < K_U; ++u) hm |= one(v[u], (u & 1) ? ts1 : ts0) ? (1u << u) : 0u;
+      if (hm) push(c, hm);
+    }
+    for (; c < W4 - 1; c += KT) if (one(fold(ldg4(c, true), c), ts0)) push(c, 1u);
+    if (tid == 0 || tid == 32) { const int ce = tid ? W4 - 1 : 0; if (one(chunk(ce, true), ts1)) push(ce, 1u); }
+  }
+  float M, ssum;
+  {
+    const uint32_t wk = __reduce_max_sync(0xffffffffu, ns_f32_orderable(bk + 0.0f));
+    float wts = ts0 + ts1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wts += __shfl_xor_sync(0xffffffffu, wts, o);
+    if (lane == 0) { sc.wmax[warp] = wk; sc.wsum[warp] = wts; }
+    __syncthreads();                                         // (also: the hit list is complete)
+    uint32_t mk = 0;
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < KW; ++w) { mk = max(mk, sc.wmax[w]); tot += sc.wsum[w]; }
+    M = key_of_pack((u64)mk << 32);
+    ssum = 4.0f * tot * k_ex2((ref - M) * c2);               // >= sum_j exp((x_j - M)/temp): four keys per chunk, each <= its maximum
+  }
+  // ---- row constants (every thread, same bits): the formulas of fast_row, with the bound in place of the estimate
+  const double thr = __ddiv_rn(1.0, (double)R);              // :141
+  const double Md = (double)M;
+  const double dm = UNIT_TEMP ? Md : __ddiv_rn(Md, P.temp);
+  const float tf = (float)P.temp;
+  const float key_th = fmaf(tf * 0.6931471805599453f, __log2f((float)(thr * (double)ssum)), M);   // p >= 1/R <= key >= M + temp ln(bound / R)
+  const float kappa_r = key_th + tf * K_BAND_EPS + 0.02f * tf;   // guard for the fp32 arithmetic of the bound
+  const float clamp_key = (float)(Md - 700.0 * P.temp);
+  const int nhit = sc.nhit;
+  const float scale2 = (float)K_NB / (M - k_c);
+  const float boff2 = M * scale2 + K_MAGIC;
+  if (!(ssum > 0.0f) || !(ssum < 3.0e38f) || !(R >= 2) || !(key_th > clamp_key) || !(M > -3.0e38f) || !(M < 3.0e38f) ||
+      nhit > K_HCAP || !(M > k_c) || !(scale2 > 0.0f) || !(scale2 < 3.0e38f) || !(fabsf(boff2) < 3.0e38f)) {
     if (tid == 0) k_defer(P, mid, row);
     return;
   }
-  // ---- sweep 2 (L2): the keys of buckets 0 .. tb, grouped by bucket
-  {
-    const uint32_t tboff = (uint32_t)tb << 2;
-    sweep(true, [&](const float4 v, int id, bool) {
-      if (fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) >= key_gather) {
-        const float xs[4] = {v.x, v.y, v.z, v.w};
+  // ---- gather (L2): the candidates = keys >= k_c of the hit chunks
+  for (int h = tid; h < nhit; h += KT) {
+    const uint32_t ent = (uint32_t)hits[h];
+    for (uint32_t hm = ent & ((1u << K_U) - 1u); hm != 0; hm &= hm - 1u) {
+      const int c = (int)(ent >> K_U) + (__ffs((int)hm) - 1) * KT, b0 = 4 * c - mis;
+      const float4 v = chunk(c, true);
+      const float xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t off = k_off(xs[j], scale, boff);
-          if (off <= tboff && (unsigned)(id + j) < (unsigned)V) {
-            const uint32_t old = atomicSub(&hist[off >> 2], 1u);        // low 16 bits: slots still free in the bucket
-            const uint32_t ex = old >> 16, pos = ex + (old & 0xffffu) - 1u;
-            if (pos < (uint32_t)K_CAP) { KEntry e; e.key = xs[j] + 0.0f; e.id = id + j; e.ex = ex; e.pad = 0u; list[pos] = e; }
-          }
+      for (int j = 0; j < 4; ++j)
+        if (xs[j] >= k_c && (unsigned)(b0 + j) < (unsigned)V) {
+          const int p = atomicAdd(&sc.ncand, 1);
+          if (p < K_CAP) { KCand e; e.key = xs[j] + 0.0f; e.id = b0 + j; cand[p] = e; }
         }
-      }
-    }, KDepth<4>());
+    }
   }
   __syncthreads();
-  // ---- order inside each bucket; exact e of the K kept tokens at their positions
+  const int nc = sc.ncand;
+  if (nc < K || nc > K_CAP) {                                // the sample bound missed (rare), or ties past the list
+    if (tid == 0) k_defer(P, mid, row);
+    return;
+  }
+  // ---- order: count histogram of the candidates over [k_c, M], grouped by bucket, exact order inside each bucket
+  {
+    const uint32_t hb = (uint32_t)__cvta_generic_to_shared(hist);
+    for (int i = tid; i < nc; i += KT)
+      asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(hb + k_off(cand[i].key, scale2, boff2)), "r"(1u) : "memory");
+  }
+  __syncthreads();
+  scan_find(K - 1, true);                                    // bucket of the last kept position
+  const int total = (int)(sc.sel_prefix + sc.sel_cnt);       // candidates in the buckets up to that one: at least K
+  if (sc.sel_bin < 0 || sc.sel_cnt > (uint32_t)K_TIE_CAP) {
+    if (tid == 0) k_defer(P, mid, row);
+    return;
+  }
+  for (int i = tid; i < nc; i += KT) {
+    const KCand cnd = cand[i];
+    const uint32_t off = k_off(cnd.key, scale2, boff2);
+    const uint32_t old = atomicSub(&hist[off >> 2], 1u);     // low 16 bits: slots still free in the bucket
+    const uint32_t ex = old >> 16, pos = ex + (old & 0xffffu) - 1u;
+    KEntry e; e.key = cnd.key; e.id = cnd.id; e.ex = ex; e.pad = 0u;
+    list[pos] = e;
+  }
+  __syncthreads();
   double* es = reinterpret_cast<double*>(hist);              // [K_TOPK_CAP]
   int* sid = reinterpret_cast<int*>(hist + 2 * K_TOPK_CAP);  // [K_TOPK_CAP]
   for (int p = tid; p < total; p += KT) {
@@ -277,9 +334,14 @@ __global__ void __launch_bounds__(KT, 2) ac_topk_stream_kernel(const __grid_cons
       if (!UNIT_TEMP) x = __ddiv_rn(x, P.temp);
       es[r] = ns_exp64_core(x - dm, c_exp_tab);
       sid[r] = me.id;
+      if (r == K - 1) sc.kth_key = me.key;
     }
   }
   __syncthreads();
+  if (!(sc.kth_key >= kappa_r)) {                            // top-k does not certainly bind (:75): the threshold form decides
+    if (tid == 0) k_defer(P, mid, row);
+    return;
+  }
   // ---- bin widths, prefix sums, overfill, selection: thread r holds the token of rank r
   const double ev = tid < K ? es[tid] : 0.0;
   double S = ev;                                             // sum of the kept e, fixed order (:146)
