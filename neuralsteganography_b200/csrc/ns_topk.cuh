@@ -3,7 +3,7 @@
 //
 // When at least topk tokens have p >= 1/range the kept set is the topk largest logits (arithmetic.py:142) and
 // nothing below them matters: no fp64 work on the row at all, and the row is read from HBM exactly ONCE with a
-// dozen instructions per 16-byte chunk.  One 512-thread CTA per row, 44 KB of shared memory, several CTAs per SM,
+// dozen instructions per 16-byte chunk.  One 512-thread CTA per row, 33 KB of shared memory, four CTAs per SM,
 // so the chain of one row hides under the sweeps of the others.
 //   sample   two chunks per thread (4096 logits, strided over the row): count histogram of the sample -> a key
 //            bound k_c that about 2.5 topk + 64 keys of the row exceed (order statistics of the sample: the
@@ -33,19 +33,18 @@ constexpr int K_MIN_VOCAB = 8192;            // the sample needs 1024 distinct i
 #define NST_U 4
 #endif
 #ifndef NST_MIN_CTAS
-#define NST_MIN_CTAS 3
+#define NST_MIN_CTAS 4
 #endif
 constexpr int K_U = NST_U;                   // chunk loads in flight per thread
 constexpr int K_MIN_CTAS = NST_MIN_CTAS;     // CTAs per SM the register budget is cut for
 constexpr int K_TIE_CAP = 256;               // keys in the boundary bucket (the order inside a bucket is quadratic)
 constexpr float K_MAGIC = 2097152.0f;        // 2^21: a float counts quarters there
 constexpr float K_BAND_EPS = 0.0009765625f;  // the guard band of the throughput kernels (F_BAND_EPS)
-static_assert(K_TOPK_CAP <= KT && K_TOPK_CAP * 12 <= K_NB * 4 && K_TOPK_CAP * 8 <= K_CAP * 16, "chain arrays live in the histogram / list areas");
-static_assert(K_HCAP * 4 <= K_CAP * 16, "the hit list lives in the list area");
+static_assert(K_TOPK_CAP <= KT && K_TOPK_CAP * 12 <= K_CAP * 8, "chain arrays live in the candidate / list areas");
+static_assert(K_HCAP * 4 <= K_CAP * 8, "the hit list lives in the list area");
 static_assert(K_U >= 1 && K_U <= 8, "hit entries carry K_U mask bits under the chunk index");
 static_assert(5 * K_TOPK_CAP / 2 + 64 + 400 <= K_CAP, "room for the spread of the candidate count");
 
-struct KEntry { float key; int id; uint32_t ex; uint32_t pad; };   // ex = first list position of the entry's bucket
 struct KCand { float key; int id; };
 struct KScal {
   u64 red[KW];
@@ -54,6 +53,11 @@ struct KScal {
   int sel_bin, res_idx, res_found, nhit, ncand;
   uint32_t sel_prefix, sel_cnt;
   float kth_key;
+  // the stream's scalars (thread 0) and the row's constants (one thread, while the others gather)
+  u64 lo, R, window;
+  double dm;
+  float M, kappa_r, clamp_key, scale2, boff2;
+  int go, slot, cursor, mlen, tok, bad;
 };
 
 __device__ __forceinline__ float k_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -70,36 +74,44 @@ __device__ __forceinline__ void k_defer(const ns_ac_params& P, int32_t* mid, int
 
 template <bool UNIT_TEMP, int MODE>
 __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __grid_constant__ ns_ac_params P, int32_t* mid) {
-  __shared__ __align__(16) uint32_t hist[K_NB];              // count histograms; later es[topk] (fp64) and sid[topk]
-  __shared__ __align__(16) KEntry list[K_CAP];               // hit chunks; candidates grouped by bucket; prefix sums of the bin widths
-  __shared__ __align__(16) KCand cand[K_CAP];                // candidates in arrival order
+  __shared__ __align__(16) uint32_t hist[K_NB];              // count histograms; then count | prefix << 16 per bucket
+  __shared__ __align__(16) KCand list[K_CAP];                // hit chunks; candidates grouped by bucket; prefix sums of the bin widths
+  __shared__ __align__(16) KCand cand[K_CAP];                // candidates in arrival order; later es[topk] (fp64) and sid[topk]
   __shared__ KScal sc;
   const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, V = P.V, K = P.topk;
-  // ---- the stream's scalars
-  int phase = P.phase ? (int)P.phase[row] : NS_PHASE_CODING;
-  if (phase == NS_PHASE_DONE) return;
-  if (MODE != MODE_ENC) phase = NS_PHASE_CODING;
-  const int slot = P.ntok ? P.ntok[row] : 0;
-  if (MODE == MODE_ENC && P.ntok && slot >= P.token_cap) {
-    if (tid == 0) { if (P.phase) P.phase[row] = NS_PHASE_DONE; if (P.status) atomicOr(&P.status[row], NS_ST_TOKEN_OVERFLOW); }
-    return;
-  }
-  if (MODE == MODE_DEC && P.ntok_total && slot >= P.ntok_total[row]) {
-    if (tid == 0 && P.phase) P.phase[row] = NS_PHASE_DONE;
-    return;
-  }
-  if (MODE == MODE_ENC && phase == NS_PHASE_TAIL) {          // finish_sent tail (:135-137): the row-resident kernel emits rank 0
-    if (tid == 0) k_defer(P, mid, row);
-    return;
-  }
-  const u64 lo = P.lo[row], R = P.hi[row] - lo;              // arithmetic.py:140
-  int cursor = 0, mlen = 0, tok = -1;
-  u64 window = 0;
-  if (MODE == MODE_ENC) {
-    cursor = P.cursor[row]; mlen = P.msg_len[row];
-    window = ns_read_bits(P.msg + (size_t)row * P.msg_stride, cursor, mlen, P.precision);   // :168-171
-  } else {
-    tok = P.token_in[(size_t)row * P.token_stride + slot];
+  // ---- the stream's scalars: one thread, handed on through shared memory at the first barrier
+  if (tid == 0) {
+    int go = 1;
+    int phase = P.phase ? (int)P.phase[row] : NS_PHASE_CODING;
+    if (phase == NS_PHASE_DONE) go = 0;
+    if (MODE != MODE_ENC) phase = NS_PHASE_CODING;
+    const int slot = P.ntok ? P.ntok[row] : 0;
+    if (go && MODE == MODE_ENC && P.ntok && slot >= P.token_cap) {
+      if (P.phase) P.phase[row] = NS_PHASE_DONE;
+      if (P.status) atomicOr(&P.status[row], NS_ST_TOKEN_OVERFLOW);
+      go = 0;
+    }
+    if (go && MODE == MODE_DEC && P.ntok_total && slot >= P.ntok_total[row]) {
+      if (P.phase) P.phase[row] = NS_PHASE_DONE;
+      go = 0;
+    }
+    if (go && MODE == MODE_ENC && phase == NS_PHASE_TAIL) {  // finish_sent tail (:135-137): the row-resident kernel emits rank 0
+      k_defer(P, mid, row);
+      go = 0;
+    }
+    sc.go = go; sc.slot = slot;
+    if (go) {
+      const u64 lo = P.lo[row];
+      sc.lo = lo; sc.R = P.hi[row] - lo;                     // arithmetic.py:140
+      if (MODE == MODE_ENC) {
+        const int cursor = P.cursor[row], mlen = P.msg_len[row];
+        sc.cursor = cursor; sc.mlen = mlen;
+        sc.window = ns_read_bits(P.msg + (size_t)row * P.msg_stride, cursor, mlen, P.precision);   // :168-171
+      } else {
+        sc.tok = P.token_in[(size_t)row * P.token_stride + slot];
+      }
+    }
+    sc.nhit = 0; sc.ncand = 0; sc.kth_key = -INFINITY; sc.bad = 0;
   }
   const float* g = P.logits + (size_t)row * (size_t)P.ld;
   const int mis = (int)(((uintptr_t)g & 15u) >> 2);
@@ -127,16 +139,15 @@ __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __
     }
     return v;
   };
-  // any chunk, the two edge chunks element-wise (-inf outside the row)
-  auto chunk = [&](int c, bool last) -> float4 {
-    if (c >= 1 && c < W4 - 1) return fold(ldg4(c, last), c);
+  // an edge chunk element-wise (-inf outside the row)
+  auto edge = [&](int c) -> float4 {
     const int b0 = 4 * c - mis;
     float4 v;
     v.x = (b0 >= 0 && b0 < V) ? g[b0] : -INFINITY;
     v.y = (b0 + 1 >= 0 && b0 + 1 < V) ? g[b0 + 1] : -INFINITY;
     v.z = (b0 + 2 >= 0 && b0 + 2 < V) ? g[b0 + 2] : -INFINITY;
     v.w = (b0 + 3 >= 0 && b0 + 3 < V) ? g[b0 + 3] : -INFINITY;
-    return fold(v, c);
+    return v;
   };
   // exclusive scan of the histogram (bucket 0 = largest keys) and the bucket holding position `pos`; the buckets
   // become count | prefix << 16 (pack) or zero
@@ -163,7 +174,6 @@ __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __
     __syncthreads();
   };
   for (int i = tid; i < K_NB; i += KT) hist[i] = 0;
-  if (tid == 0) { sc.nhit = 0; sc.ncand = 0; sc.kth_key = -INFINITY; }
   // ---- sample: two chunks per thread, strided over the row -> bucket range, reference of the bound, key bound k_c
   float k_c, ref;
   {
@@ -177,7 +187,8 @@ __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __
     const uint32_t ra = __reduce_max_sync(0xffffffffu, ns_f32_orderable(sb));
     const uint32_t rb = __reduce_min_sync(0xffffffffu, ns_f32_orderable(sl));
     if (lane == 0) { sc.smax[warp] = ra; sc.smin[warp] = rb; }
-    __syncthreads();                                         // (also: the histogram is clear)
+    __syncthreads();                                         // (also: the histogram is clear, the stream's scalars are there)
+    if (!sc.go) return;
     uint32_t ga = 0, gb = 0xffffffffu;
 #pragma unroll
     for (int w = 0; w < KW; ++w) { ga = max(ga, sc.smax[w]); gb = min(gb, sc.smin[w]); }
@@ -209,9 +220,9 @@ __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __
   }
   // ---- the sweep (HBM, once): chunk maxima -> row maximum, upper bound of the normaliser, hit list
   const float c2 = (float)(1.4426950408889634 / P.temp);     // log2(e)/temp
-  float bk = -INFINITY, ts0 = 0.f, ts1 = 0.f;
   int* hits = reinterpret_cast<int*>(list);                  // [K_HCAP]
   {
+    float bk = -INFINITY, ts0 = 0.f, ts1 = 0.f;
     const float nrc = -ref * c2;
     auto one = [&](const float4 v, float& ts) -> bool {
       const float m = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
@@ -243,61 +254,64 @@ __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __
       if (hm) push(c, hm);
     }
     for (; c < W4 - 1; c += KT) if (one(fold(ldg4(c, true), c), ts0)) push(c, 1u);
-    if (tid == 0 || tid == 32) { const int ce = tid ? W4 - 1 : 0; if (one(chunk(ce, true), ts1)) push(ce, 1u); }
-  }
-  float M, ssum;
-  {
+    if (tid == 0 || tid == 32) { const int ce = tid ? W4 - 1 : 0; if (one(fold(edge(ce), ce), ts1)) push(ce, 1u); }
     const uint32_t wk = __reduce_max_sync(0xffffffffu, ns_f32_orderable(bk + 0.0f));
     float wts = ts0 + ts1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wts += __shfl_xor_sync(0xffffffffu, wts, o);
     if (lane == 0) { sc.wmax[warp] = wk; sc.wsum[warp] = wts; }
-    __syncthreads();                                         // (also: the hit list is complete)
+  }
+  __syncthreads();                                           // the hit list and the warps' maxima / sums are complete
+  // ---- row constants: one thread (the formulas of fast_row, with the bound in place of the estimate) ...
+  if (tid == KT - 32) {
     uint32_t mk = 0;
     float tot = 0.f;
 #pragma unroll
     for (int w = 0; w < KW; ++w) { mk = max(mk, sc.wmax[w]); tot += sc.wsum[w]; }
-    M = key_of_pack((u64)mk << 32);
-    ssum = 4.0f * tot * k_ex2((ref - M) * c2);               // >= sum_j exp((x_j - M)/temp): four keys per chunk, each <= its maximum
+    const float M = key_of_pack((u64)mk << 32);
+    const float ssum = 4.0f * tot * k_ex2((ref - M) * c2);   // >= sum_j exp((x_j - M)/temp): four keys per chunk, each <= its maximum
+    const u64 R = sc.R;
+    const double thr = __ddiv_rn(1.0, (double)R);            // :141
+    const double Md = (double)M;
+    const float tf = (float)P.temp;
+    const float key_th = fmaf(tf * 0.6931471805599453f, __log2f((float)(thr * (double)ssum)), M);   // p >= 1/R <= key >= M + temp ln(bound / R)
+    const float clamp_key = (float)(Md - 700.0 * P.temp);
+    const float scale2 = (float)K_NB / (M - k_c);
+    const float boff2 = M * scale2 + K_MAGIC;
+    sc.M = M;
+    sc.dm = UNIT_TEMP ? Md : __ddiv_rn(Md, P.temp);
+    sc.kappa_r = key_th + tf * K_BAND_EPS + 0.02f * tf;      // guard for the fp32 arithmetic of the bound
+    sc.clamp_key = clamp_key; sc.scale2 = scale2; sc.boff2 = boff2;
+    sc.bad = (!(ssum > 0.0f) || !(ssum < 3.0e38f) || !(R >= 2) || !(key_th > clamp_key) || !(M > -3.0e38f) || !(M < 3.0e38f) ||
+              !(M > k_c) || !(scale2 > 0.0f) || !(scale2 < 3.0e38f) || !(fabsf(boff2) < 3.0e38f)) ? 1 : 0;
   }
-  // ---- row constants (every thread, same bits): the formulas of fast_row, with the bound in place of the estimate
-  const double thr = __ddiv_rn(1.0, (double)R);              // :141
-  const double Md = (double)M;
-  const double dm = UNIT_TEMP ? Md : __ddiv_rn(Md, P.temp);
-  const float tf = (float)P.temp;
-  const float key_th = fmaf(tf * 0.6931471805599453f, __log2f((float)(thr * (double)ssum)), M);   // p >= 1/R <= key >= M + temp ln(bound / R)
-  const float kappa_r = key_th + tf * K_BAND_EPS + 0.02f * tf;   // guard for the fp32 arithmetic of the bound
-  const float clamp_key = (float)(Md - 700.0 * P.temp);
-  const int nhit = sc.nhit;
-  const float scale2 = (float)K_NB / (M - k_c);
-  const float boff2 = M * scale2 + K_MAGIC;
-  if (!(ssum > 0.0f) || !(ssum < 3.0e38f) || !(R >= 2) || !(key_th > clamp_key) || !(M > -3.0e38f) || !(M < 3.0e38f) ||
-      nhit > K_HCAP || !(M > k_c) || !(scale2 > 0.0f) || !(scale2 < 3.0e38f) || !(fabsf(boff2) < 3.0e38f)) {
-    if (tid == 0) k_defer(P, mid, row);
-    return;
-  }
-  // ---- gather (L2): the candidates = keys >= k_c of the hit chunks
-  for (int h = tid; h < nhit; h += KT) {
-    const uint32_t ent = (uint32_t)hits[h];
-    for (uint32_t hm = ent & ((1u << K_U) - 1u); hm != 0; hm &= hm - 1u) {
-      const int c = (int)(ent >> K_U) + (__ffs((int)hm) - 1) * KT, b0 = 4 * c - mis;
-      const float4 v = chunk(c, true);
-      const float xs[4] = {v.x, v.y, v.z, v.w};
+  // ---- ... while the others gather (L2) the candidates = keys >= k_c of the hit chunks
+  {
+    const int nhit = min(sc.nhit, K_HCAP);
+    for (int h = tid; h < nhit; h += KT) {
+      const uint32_t ent = (uint32_t)hits[h];
+      for (uint32_t hm = ent & ((1u << K_U) - 1u); hm != 0; hm &= hm - 1u) {
+        const int c = (int)(ent >> K_U) + (__ffs((int)hm) - 1) * KT, b0 = 4 * c - mis;
+        const float4 v = (c >= 1 && c < W4 - 1) ? ldg4(c, true) : edge(c);
+        const float xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (xs[j] >= k_c && (unsigned)(b0 + j) < (unsigned)V) {
-          const int p = atomicAdd(&sc.ncand, 1);
-          if (p < K_CAP) { KCand e; e.key = xs[j] + 0.0f; e.id = b0 + j; cand[p] = e; }
-        }
+        for (int j = 0; j < 4; ++j)
+          if (xs[j] >= k_c && (unsigned)(b0 + j) < (unsigned)V && b0 + j != mk0 && b0 + j != mk1) {
+            const int p = atomicAdd(&sc.ncand, 1);
+            if (p < K_CAP) { KCand e; e.key = xs[j] + 0.0f; e.id = b0 + j; cand[p] = e; }
+          }
+      }
     }
   }
   __syncthreads();
   const int nc = sc.ncand;
-  if (nc < K || nc > K_CAP) {                                // the sample bound missed (rare), or ties past the list
+  // not carried: constants out of range, hit list full, the sample bound missed (rare) or ties past the list
+  if (sc.bad || sc.nhit > K_HCAP || nc < K || nc > K_CAP) {
     if (tid == 0) k_defer(P, mid, row);
     return;
   }
   // ---- order: count histogram of the candidates over [k_c, M], grouped by bucket, exact order inside each bucket
+  const float scale2 = sc.scale2, boff2 = sc.boff2;
   {
     const uint32_t hb = (uint32_t)__cvta_generic_to_shared(hist);
     for (int i = tid; i < nc; i += KT)
@@ -314,73 +328,80 @@ __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __
     const KCand cnd = cand[i];
     const uint32_t off = k_off(cnd.key, scale2, boff2);
     const uint32_t old = atomicSub(&hist[off >> 2], 1u);     // low 16 bits: slots still free in the bucket
-    const uint32_t ex = old >> 16, pos = ex + (old & 0xffffu) - 1u;
-    KEntry e; e.key = cnd.key; e.id = cnd.id; e.ex = ex; e.pad = 0u;
-    list[pos] = e;
+    list[(old >> 16) + (old & 0xffffu) - 1u] = cnd;
+  }
+  __syncthreads();                                           // (the buckets now hold prefix << 16: where each bucket starts)
+  double* es = reinterpret_cast<double*>(cand);              // [K_TOPK_CAP]
+  int* sid = reinterpret_cast<int*>(cand + K_TOPK_CAP);      // [K_TOPK_CAP]
+  {
+    const float clamp_key = sc.clamp_key;
+    const double dm = sc.dm;
+    for (int p = tid; p < total; p += KT) {
+      const KCand me = list[p];
+      const uint32_t b = k_off(me.key, scale2, boff2) >> 2;
+      const int ex = (int)(hist[b] >> 16), end = b + 1 < (uint32_t)K_NB ? (int)(hist[b + 1] >> 16) : nc;
+      int r = ex;
+      for (int o = ex; o < end; ++o) {
+        const KCand ot = list[o];
+        r += (ot.key > me.key || (ot.key == me.key && ot.id < me.id)) ? 1 : 0;   // coder order: key, then lower id
+      }
+      if (r < K) {
+        double x = (double)fmaxf(me.key, clamp_key);         // (double(x)/temp) - (double(max)/temp), :128-130
+        if (!UNIT_TEMP) x = __ddiv_rn(x, P.temp);
+        es[r] = ns_exp64_core(x - dm, c_exp_tab);
+        sid[r] = me.id;
+        if (r == K - 1) sc.kth_key = me.key;
+      }
+    }
   }
   __syncthreads();
-  double* es = reinterpret_cast<double*>(hist);              // [K_TOPK_CAP]
-  int* sid = reinterpret_cast<int*>(hist + 2 * K_TOPK_CAP);  // [K_TOPK_CAP]
-  for (int p = tid; p < total; p += KT) {
-    const KEntry me = list[p];
-    int r = (int)me.ex;
-    for (int o = (int)me.ex; o < total; ++o) {
-      const KEntry ot = list[o];
-      if (ot.ex != me.ex) break;
-      r += (ot.key > me.key || (ot.key == me.key && ot.id < me.id)) ? 1 : 0;   // coder order: key, then lower id
-    }
-    if (r < K) {
-      double x = (double)fmaxf(me.key, clamp_key);           // (double(x)/temp) - (double(max)/temp), :128-130
-      if (!UNIT_TEMP) x = __ddiv_rn(x, P.temp);
-      es[r] = ns_exp64_core(x - dm, c_exp_tab);
-      sid[r] = me.id;
-      if (r == K - 1) sc.kth_key = me.key;
-    }
-  }
-  __syncthreads();
-  if (!(sc.kth_key >= kappa_r)) {                            // top-k does not certainly bind (:75): the threshold form decides
+  if (!(sc.kth_key >= sc.kappa_r)) {                         // top-k does not certainly bind (:75): the threshold form decides
     if (tid == 0) k_defer(P, mid, row);
     return;
   }
-  // ---- bin widths, prefix sums, overfill, selection: thread r holds the token of rank r
+  // ---- bin widths, prefix sums, overfill, selection: thread r holds the token of rank r; only the warps that hold a
+  // rank go on (named barrier over those warps)
+  const int nwt = ((K + 31) >> 5) << 5;                      // threads of the warps holding a rank
+  if (tid >= nwt) return;
+  auto tail_sync = [&]() { asm volatile("bar.sync 1, %0;" :: "r"(nwt) : "memory"); };
+  const int NWK = nwt >> 5;
+  const u64 lo = sc.lo, R = sc.R;
   const double ev = tid < K ? es[tid] : 0.0;
   double S = ev;                                             // sum of the kept e, fixed order (:146)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) S = S + __shfl_xor_sync(0xffffffffu, S, o);
   if (lane == 0) sc.red[warp] = (u64)__double_as_longlong(S);
-  __syncthreads();
+  tail_sync();
   S = __longlong_as_double((long long)sc.red[0]);
-#pragma unroll
-  for (int w = 1; w < KW; ++w) S = S + __longlong_as_double((long long)sc.red[w]);
+  for (int w = 1; w < NWK; ++w) S = S + __longlong_as_double((long long)sc.red[w]);   // warps without a rank add 0.0: same bits as all KW
   const double C = __ddiv_rn((double)R, S);
   const u64 q = tid < K ? (u64)__double2ll_rn(ev * C) : 0ull;   // :146-149
   u64 cum = q;                                               // inclusive prefix sums over the ranks (:150)
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const u64 t = __shfl_up_sync(0xffffffffu, cum, o); if (lane >= o) cum += t; }
-  __syncthreads();                                           // red of the sum is consumed
+  tail_sync();                                               // red of the sum is consumed
   if (lane == 31) sc.red[warp] = cum;
-  __syncthreads();
+  tail_sync();
   u64 Q = 0;
   {
     u64 wo = 0;
-#pragma unroll
-    for (int w = 0; w < KW; ++w) { const u64 x = sc.red[w]; if (w < warp) wo += x; Q += x; }
+    for (int w = 0; w < NWK; ++w) { const u64 x = sc.red[w]; if (w < warp) wo += x; Q += x; }
     cum += wo;
   }
   u64* cums = reinterpret_cast<u64*>(list);                  // [K_TOPK_CAP]; the gathered list is no longer needed
   if (tid < K) cums[tid] = cum;
-  __syncthreads();
+  tail_sync();
   // overfill (:153-158): drop the ranks from the first prefix sum above the range on
   int kk = K;
   u64 slack;
   if (Q > R) {
     if (tid < K && cum > R && (tid == 0 || cums[tid - 1] <= R)) sc.res_idx = tid;
-    __syncthreads();
+    tail_sync();
     kk = sc.res_idx;
     slack = R - (kk > 0 ? cums[kk - 1] : 0ull);
-    __syncthreads();
+    tail_sync();
     if (tid == 0) sc.res_idx = K;
-    __syncthreads();
+    tail_sync();
   } else {
     slack = R - Q;
   }
@@ -388,20 +409,21 @@ __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __
   const u64 my_lo = (tid > 0 && tid < K) ? cums[tid - 1] + slack : 0ull;
   const u64 my_hi = cum + slack;
   if (MODE == MODE_ENC) {
-    const u64 m_rel = window - lo;                           // next `precision` message bits (:168-171)
+    const u64 m_rel = sc.window - lo;                        // next `precision` message bits (:168-171)
     if (tid < kk && my_lo <= m_rel && m_rel < my_hi) sc.res_idx = tid;   // :172 (empty bins never match)
-    __syncthreads();
+    tail_sync();
     const int r = sc.res_idx;
     if (tid == (r < kk ? r : 0)) {
       if (r >= kk && P.status) atomicOr(&P.status[row], NS_ST_BIN_OVERFLOW);   // cannot happen: the bins tile the range
-      finish_encode(P, row, slot, sid[tid], lo + my_lo, lo + my_hi, (u64)K, Q, cursor, mlen);   // :175-176
+      finish_encode(P, row, sc.slot, sid[tid], lo + my_lo, lo + my_hi, (u64)K, Q, sc.cursor, sc.mlen);   // :175-176
     }
   } else {
+    const int tok = sc.tok;
     const bool tok_ok = tok >= 0 && tok < V;
     if (tid < kk && tok_ok && sid[tid] == tok) { sc.res_idx = tid; sc.res_found = 1; }
-    __syncthreads();
+    tail_sync();
     const bool in_range = sc.res_found != 0;
     const int r = in_range ? sc.res_idx : 0;                 // :342 / :347-348: unknown tokens are coded as rank 0
-    if (tid == r) finish_decode(P, row, slot, in_range || !tok_ok, lo + my_lo, lo + my_hi, (u64)K, Q);
+    if (tid == r) finish_decode(P, row, sc.slot, in_range || !tok_ok, lo + my_lo, lo + my_hi, (u64)K, Q);
   }
 }
