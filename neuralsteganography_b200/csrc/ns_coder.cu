@@ -587,7 +587,7 @@ int dispatch(const ns_ac_params* p, u64* dbg_q, u64* dbg_meta, void* stream) {
   const bool lean = !rank && p->variant == 0 && p->V >= nsl::L_MIN_VOCAB && p->V <= nsl::L_MAX_VOCAB;
   // rank form: the sweep kernel first (when the caller gave it a work list), then the row-resident kernel on the rows
   // that one queued (not certainly in rank form, finish_sent tails, degenerate rows)
-  const bool topk_sweep = rank && p->variant == 0 && p->rank_ws != nullptr && p->V >= nst::K_MIN_VOCAB && p->topk <= nst::K_TOPK_CAP;
+  const bool topk_sweep = rank && p->variant == 0 && p->rank_ws != nullptr && nst::k_shape_ok(p->V, p->topk);
   if (topk_sweep) {
     rc = (p->temp == 1.0) ? launch_topk<true, M2>(p, st) : launch_topk<false, M2>(p, st);
     if (rc != NS_OK) return rc;

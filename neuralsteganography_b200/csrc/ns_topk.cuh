@@ -37,6 +37,7 @@ constexpr int K_MIN_VOCAB = 8192;            // the sample needs 1024 distinct i
 #endif
 constexpr int K_U = NST_U;                   // chunk loads in flight per thread
 constexpr int K_MIN_CTAS = NST_MIN_CTAS;     // CTAs per SM the register budget is cut for
+constexpr int K_JMAX = 8;                    // rounds of the sample selection (the host sends smaller V / larger topk to ns_fast.cuh)
 constexpr int K_TIE_CAP = 256;               // keys in the boundary bucket (the order inside a bucket is quadratic)
 constexpr float K_MAGIC = 2097152.0f;        // 2^21: a float counts quarters there
 constexpr float K_BAND_EPS = 0.0009765625f;  // the guard band of the throughput kernels (F_BAND_EPS)
@@ -45,6 +46,10 @@ static_assert(K_HCAP * 4 <= K_CAP * 8, "the hit list lives in the list area");
 static_assert(K_U >= 1 && K_U <= 8, "hit entries carry K_U mask bits under the chunk index");
 static_assert(5 * K_TOPK_CAP / 2 + 64 + 400 <= K_CAP, "room for the spread of the candidate count");
 
+// shapes the sweep kernel takes: the sample selection needs its rank within K_JMAX rounds
+inline bool k_shape_ok(int V, int K) {
+  return V >= K_MIN_VOCAB && K >= 2 && K <= K_TOPK_CAP && (long long)((5 * K) / 2 + 64) * 256 + V / 2 < (long long)(K_JMAX + 1) * V;
+}
 struct KCand { float key; int id; };
 struct KScal {
   u64 red[KW];
@@ -55,9 +60,9 @@ struct KScal {
   float kth_key;
   // the stream's scalars (thread 0) and the row's constants (one thread, while the others gather)
   u64 lo, R, window;
-  double dm;
+  double dm, thr;
   float M, kappa_r, clamp_key, scale2, boff2;
-  int go, slot, cursor, mlen, tok, bad;
+  int go, slot, cursor, mlen, tok, bad, bad2;
 };
 
 __device__ __forceinline__ float k_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -79,40 +84,6 @@ __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __
   __shared__ __align__(16) KCand cand[K_CAP];                // candidates in arrival order; later es[topk] (fp64) and sid[topk]
   __shared__ KScal sc;
   const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, V = P.V, K = P.topk;
-  // ---- the stream's scalars: one thread, handed on through shared memory at the first barrier
-  if (tid == 0) {
-    int go = 1;
-    int phase = P.phase ? (int)P.phase[row] : NS_PHASE_CODING;
-    if (phase == NS_PHASE_DONE) go = 0;
-    if (MODE != MODE_ENC) phase = NS_PHASE_CODING;
-    const int slot = P.ntok ? P.ntok[row] : 0;
-    if (go && MODE == MODE_ENC && P.ntok && slot >= P.token_cap) {
-      if (P.phase) P.phase[row] = NS_PHASE_DONE;
-      if (P.status) atomicOr(&P.status[row], NS_ST_TOKEN_OVERFLOW);
-      go = 0;
-    }
-    if (go && MODE == MODE_DEC && P.ntok_total && slot >= P.ntok_total[row]) {
-      if (P.phase) P.phase[row] = NS_PHASE_DONE;
-      go = 0;
-    }
-    if (go && MODE == MODE_ENC && phase == NS_PHASE_TAIL) {  // finish_sent tail (:135-137): the row-resident kernel emits rank 0
-      k_defer(P, mid, row);
-      go = 0;
-    }
-    sc.go = go; sc.slot = slot;
-    if (go) {
-      const u64 lo = P.lo[row];
-      sc.lo = lo; sc.R = P.hi[row] - lo;                     // arithmetic.py:140
-      if (MODE == MODE_ENC) {
-        const int cursor = P.cursor[row], mlen = P.msg_len[row];
-        sc.cursor = cursor; sc.mlen = mlen;
-        sc.window = ns_read_bits(P.msg + (size_t)row * P.msg_stride, cursor, mlen, P.precision);   // :168-171
-      } else {
-        sc.tok = P.token_in[(size_t)row * P.token_stride + slot];
-      }
-    }
-    sc.nhit = 0; sc.ncand = 0; sc.kth_key = -INFINITY; sc.bad = 0;
-  }
   const float* g = P.logits + (size_t)row * (size_t)P.ld;
   const int mis = (int)(((uintptr_t)g & 15u) >> 2);
   const int W4 = (mis + V + 3) >> 2;
@@ -120,14 +91,20 @@ __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __
   const int mk0 = (P.mask_id[0] >= 0 && P.mask_id[0] < V) ? P.mask_id[0] : -8;
   const int mk1 = (P.mask_id[1] >= 0 && P.mask_id[1] < V) ? P.mask_id[1] : -8;
   const int mc0 = (mk0 + mis) >> 2, mc1 = (mk1 + mis) >> 2;
-  u64 pol_last, pol_first;                                   // L2 eviction policies for the row's lines
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
-  auto ldg4 = [&](int c, bool last) -> float4 {
+  // (no L2 eviction hints: a policy operand costs the sweep loop a descriptor set-up per load, and the few chunks
+  // that are read twice -- the sample, the hit chunks -- come back from L2 within microseconds anyway)
+  auto ldg4 = [&](int c, bool) -> float4 {
     float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(g4 + c), "l"(last ? pol_first : pol_last));
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(g4 + c));
     return v;
+  };
+  // slot counter in shared memory, one plain atomic per calling thread (the compiler's warp-aggregated form of
+  // atomicAdd costs twenty instructions on a path nearly every warp takes for two or three of its lanes)
+  auto take_slot = [&](int* counter) -> int {
+    int old;
+    asm volatile("atom.shared.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(counter)) : "memory");   // (inc: ptxas turns add-1 into the aggregated form)
+    return old;
   };
   // forbidden tokens (arithmetic.py:124-125): probability exactly 0 -- the logits are read-only, so on the fly
   auto fold = [&](float4 v, int c) -> float4 {
@@ -174,46 +151,74 @@ __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __
     __syncthreads();
   };
   for (int i = tid; i < K_NB; i += KT) hist[i] = 0;
-  // ---- sample: two chunks per thread, strided over the row -> bucket range, reference of the bound, key bound k_c
+  // ---- sample: two chunks per thread, strided over the row -> reference of the bound, key bound k_c
   float k_c, ref;
   {
     const int NI = W4 - 2;                                   // interior chunks 1 .. W4-2 (>= 2 KT: K_MIN_VOCAB)
     const int cs0 = 1 + (int)(((long long)tid * NI) >> 10), cs1 = 1 + (int)(((long long)(tid + KT) * NI) >> 10);
-    const float4 a = fold(ldg4(cs0, false), cs0), b = fold(ldg4(cs1, false), cs1);
-    const float xs[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    float sb = -INFINITY, sl = INFINITY;
+    float4 a = ldg4(cs0, false), b = ldg4(cs1, false);
+    // ---- the stream's scalars: three threads of three warps (loads issued together, behind the sample loads), handed
+    // on through shared memory at the first barrier
+    if (tid == 0) {                                          // may the row be coded at all; slot, observed token
+      const int ph0 = P.phase ? (int)P.phase[row] : NS_PHASE_CODING;
+      const int slot = P.ntok ? P.ntok[row] : 0;
+      int ntot = 0x7fffffff;
+      if (MODE == MODE_DEC && P.ntok_total) ntot = P.ntok_total[row];
+      int go = 1;
+      if (ph0 == NS_PHASE_DONE) go = 0;
+      const int phase = MODE == MODE_ENC ? ph0 : NS_PHASE_CODING;
+      if (go && MODE == MODE_ENC && P.ntok && slot >= P.token_cap) {
+        if (P.phase) P.phase[row] = NS_PHASE_DONE;
+        if (P.status) atomicOr(&P.status[row], NS_ST_TOKEN_OVERFLOW);
+        go = 0;
+      }
+      if (go && MODE == MODE_DEC && P.ntok_total && slot >= ntot) {
+        if (P.phase) P.phase[row] = NS_PHASE_DONE;
+        go = 0;
+      }
+      if (go && MODE == MODE_ENC && phase == NS_PHASE_TAIL) {  // finish_sent tail (:135-137): the row-resident kernel emits rank 0
+        k_defer(P, mid, row);
+        go = 0;
+      }
+      sc.go = go; sc.slot = slot;
+      if (go && MODE != MODE_ENC) sc.tok = P.token_in[(size_t)row * P.token_stride + slot];
+      sc.nhit = 0; sc.ncand = 0; sc.kth_key = -INFINITY;
+    } else if (tid == 32) {                                  // the interval
+      const u64 lo = P.lo[row], R = P.hi[row] - lo;          // arithmetic.py:140
+      sc.lo = lo; sc.R = R;
+      sc.thr = __ddiv_rn(1.0, (double)R);                    // :141
+    } else if (tid == 64 && MODE == MODE_ENC) {              // the next `precision` message bits
+      const int cursor = P.cursor[row], mlen = P.msg_len[row];
+      sc.cursor = cursor; sc.mlen = mlen;
+      sc.window = ns_read_bits(P.msg + (size_t)row * P.msg_stride, cursor, mlen, P.precision);   // :168-171
+    }
+    a = fold(a, cs0); b = fold(b, cs1);
+    // j-th largest of the warp's 256 sample keys (ties struck out together), j ~ (2.5 K + 64) 256 / V: about
+    // 2.5 K + 64 keys of the row exceed it; the mean over the warps has a sixteenth of one warp's variance
+    uint32_t ks[8] = {ns_f32_orderable(a.x), ns_f32_orderable(a.y), ns_f32_orderable(a.z), ns_f32_orderable(a.w),
+                      ns_f32_orderable(b.x), ns_f32_orderable(b.y), ns_f32_orderable(b.z), ns_f32_orderable(b.w)};
+    int jr = (((5 * K) / 2 + 64) * (8 * 32) + V / 2) / V;
+    jr = jr < 1 ? 1 : (jr > K_JMAX ? K_JMAX : jr);
+    uint32_t top = 0, cur = 0;
+    for (int r = 0; r < jr; ++r) {
+      uint32_t m = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { sb = fmaxf(sb, xs[j]); sl = fminf(sl, xs[j] > -1e9f ? xs[j] : INFINITY); }
-    const uint32_t ra = __reduce_max_sync(0xffffffffu, ns_f32_orderable(sb));
-    const uint32_t rb = __reduce_min_sync(0xffffffffu, ns_f32_orderable(sl));
-    if (lane == 0) { sc.smax[warp] = ra; sc.smin[warp] = rb; }
+      for (int i = 0; i < 8; ++i) m = max(m, ks[i]);
+      cur = __reduce_max_sync(0xffffffffu, m);
+      if (r == 0) top = cur;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ks[i] = ks[i] == cur ? 0u : ks[i];
+    }
+    if (lane == 0) { sc.smax[warp] = top; sc.smin[warp] = cur; }
     __syncthreads();                                         // (also: the histogram is clear, the stream's scalars are there)
     if (!sc.go) return;
-    uint32_t ga = 0, gb = 0xffffffffu;
+    uint32_t ga = 0;
+    float ksum = 0.f;
 #pragma unroll
-    for (int w = 0; w < KW; ++w) { ga = max(ga, sc.smax[w]); gb = min(gb, sc.smin[w]); }
-    float smax = key_of_pack((u64)ga << 32), smin = key_of_pack((u64)gb << 32);
-    if (!(smax > -3.0e38f) || !(smax < 3.0e38f) || !(smin > -3.0e38f) || !(smin < 3.0e38f)) { smax = 1.0f; smin = -1.0f; }
-    float span = smax - smin;
-    if (!(span > 0.0f)) span = 1.0f;
-    const float hi_p = smax + 0.001f * span, lo_p = smin - 0.001f * span;
-    float scale = (float)K_NB / (hi_p - lo_p);
-    float boff = hi_p * scale + K_MAGIC;
-    if (!(scale > 0.0f) || !(scale < 3.0e38f) || !(fabsf(boff) < 3.0e38f)) { scale = 0.0f; boff = K_MAGIC; }
-    ref = smax;
-    const uint32_t hb = (uint32_t)__cvta_generic_to_shared(hist);
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(hb + k_off(xs[j], scale, boff)), "r"(1u) : "memory");
-    __syncthreads();
-    // sample rank whose key about 2.5 K + 64 keys of the row exceed (the sample holds 8 KT of the V logits)
-    const int want = (5 * K) / 2 + 64;
-    const int rs = (int)(((long long)want * (8 * KT) + V - 1) / V);
-    scan_find(rs - 1, false);                                // (leaves the histogram clear)
-    const int tb = sc.sel_bin;
-    // every key of bucket b satisfies (hi_p - k) scale < b + 7/8; one more bucket absorbs the rounding of the offset
-    k_c = hi_p - ((float)tb + 2.0f) / scale;
-    if (tb < 0 || !(scale > 0.0f) || !(k_c > -3.0e38f) || !(k_c < 3.0e38f)) {
+    for (int w = 0; w < KW; ++w) { ga = max(ga, sc.smax[w]); ksum += key_of_pack((u64)sc.smin[w] << 32); }
+    ref = key_of_pack((u64)ga << 32);
+    k_c = ksum * (1.0f / (float)KW);
+    if (!(ref > -3.0e38f) || !(ref < 3.0e38f) || !(k_c > -3.0e38f) || !(k_c < 3.0e38f)) {
       if (tid == 0) k_defer(P, mid, row);
       return;
     }
@@ -232,7 +237,7 @@ __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __
     };
     // hit list entry: first chunk << K_U | mask of the thread's chunks c + u KT holding a candidate
     auto push = [&](int c, uint32_t hm) {
-      const int p = atomicAdd(&sc.nhit, 1);
+      const int p = take_slot(&sc.nhit);
       if (p < K_HCAP) hits[p] = (int)(((uint32_t)c << K_U) | hm);
     };
     // interior chunk c belongs to thread (c - 1) mod KT; the (at most two) chunks with a forbidden id are folded by
@@ -262,28 +267,32 @@ __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __
     if (lane == 0) { sc.wmax[warp] = wk; sc.wsum[warp] = wts; }
   }
   __syncthreads();                                           // the hit list and the warps' maxima / sums are complete
-  // ---- row constants: one thread (the formulas of fast_row, with the bound in place of the estimate) ...
-  if (tid == KT - 32) {
+  // ---- row constants: two threads of two warps (the formulas of fast_row, with the bound in place of the estimate) ...
+  if (tid == KT - 32) {                                      // bound of the normaliser -> key above which p >= 1/R for certain
     uint32_t mk = 0;
     float tot = 0.f;
 #pragma unroll
     for (int w = 0; w < KW; ++w) { mk = max(mk, sc.wmax[w]); tot += sc.wsum[w]; }
     const float M = key_of_pack((u64)mk << 32);
     const float ssum = 4.0f * tot * k_ex2((ref - M) * c2);   // >= sum_j exp((x_j - M)/temp): four keys per chunk, each <= its maximum
-    const u64 R = sc.R;
-    const double thr = __ddiv_rn(1.0, (double)R);            // :141
-    const double Md = (double)M;
     const float tf = (float)P.temp;
-    const float key_th = fmaf(tf * 0.6931471805599453f, __log2f((float)(thr * (double)ssum)), M);   // p >= 1/R <= key >= M + temp ln(bound / R)
-    const float clamp_key = (float)(Md - 700.0 * P.temp);
+    const float key_th = fmaf(tf * 0.6931471805599453f, __log2f((float)(sc.thr * (double)ssum)), M);   // p >= 1/R <= key >= M + temp ln(bound / R)
+    const float clamp_key = (float)((double)M - 700.0 * P.temp);
+    sc.kappa_r = key_th + tf * K_BAND_EPS + 0.02f * tf;      // guard for the fp32 arithmetic of the bound
+    sc.bad = (!(ssum > 0.0f) || !(ssum < 3.0e38f) || !(sc.R >= 2) || !(key_th > clamp_key) || !(M > -3.0e38f) || !(M < 3.0e38f)) ? 1 : 0;
+  } else if (tid == KT - 64) {                               // maximum -> bucket function of the candidates, exponent offset
+    uint32_t mk = 0;
+#pragma unroll
+    for (int w = 0; w < KW; ++w) mk = max(mk, sc.wmax[w]);
+    const float M = key_of_pack((u64)mk << 32);
+    const double Md = (double)M;
     const float scale2 = (float)K_NB / (M - k_c);
     const float boff2 = M * scale2 + K_MAGIC;
     sc.M = M;
     sc.dm = UNIT_TEMP ? Md : __ddiv_rn(Md, P.temp);
-    sc.kappa_r = key_th + tf * K_BAND_EPS + 0.02f * tf;      // guard for the fp32 arithmetic of the bound
-    sc.clamp_key = clamp_key; sc.scale2 = scale2; sc.boff2 = boff2;
-    sc.bad = (!(ssum > 0.0f) || !(ssum < 3.0e38f) || !(R >= 2) || !(key_th > clamp_key) || !(M > -3.0e38f) || !(M < 3.0e38f) ||
-              !(M > k_c) || !(scale2 > 0.0f) || !(scale2 < 3.0e38f) || !(fabsf(boff2) < 3.0e38f)) ? 1 : 0;
+    sc.clamp_key = (float)(Md - 700.0 * P.temp);
+    sc.scale2 = scale2; sc.boff2 = boff2;
+    sc.bad2 = (!(M > k_c) || !(scale2 > 0.0f) || !(scale2 < 3.0e38f) || !(fabsf(boff2) < 3.0e38f)) ? 1 : 0;
   }
   // ---- ... while the others gather (L2) the candidates = keys >= k_c of the hit chunks
   {
@@ -297,7 +306,7 @@ __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (xs[j] >= k_c && (unsigned)(b0 + j) < (unsigned)V && b0 + j != mk0 && b0 + j != mk1) {
-            const int p = atomicAdd(&sc.ncand, 1);
+            const int p = take_slot(&sc.ncand);
             if (p < K_CAP) { KCand e; e.key = xs[j] + 0.0f; e.id = b0 + j; cand[p] = e; }
           }
       }
@@ -306,7 +315,7 @@ __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __
   __syncthreads();
   const int nc = sc.ncand;
   // not carried: constants out of range, hit list full, the sample bound missed (rare) or ties past the list
-  if (sc.bad || sc.nhit > K_HCAP || nc < K || nc > K_CAP) {
+  if (sc.bad || sc.bad2 || sc.nhit > K_HCAP || nc < K || nc > K_CAP) {
     if (tid == 0) k_defer(P, mid, row);
     return;
   }

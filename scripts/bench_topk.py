@@ -23,8 +23,9 @@ for force in (False, True):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     handed = int(((st.status & 4) != 0).sum().item())
-    print("topk %d temp %.2f %s: %.3f ms/step  %.2f M tok/s  %.2f bits/token  rows ever handed to the exact kernel: %d of %d"
+    deferred = int(((st.status & 16) != 0).sum().item())
+    print("topk %d temp %.2f %s: %.3f ms/step  %.2f M tok/s  %.2f bits/token  rows ever handed to the exact kernel: %d of %d, ever left by the sweep kernel to the row-resident one: %d"
           % (TOPK, TEMP, "exact kernel only" if force else "throughput kernel", ms, B / ms / 1e3,
-             (int(st.cursor.sum().item()) - c0) / (B * n), handed, B))
+             (int(st.cursor.sum().item()) - c0) / (B * n), handed, B, deferred))
     if not force: toks_fast = st.tokens.clone()
     else: print("   same tokens as the throughput kernel on the common steps:", bool((toks_fast[:, :8] == st.tokens[:, :8]).all().item()))
