@@ -41,6 +41,9 @@ static_assert(sizeof(Scalars) <= 1024, "scalar block too large");
 constexpr int MAX_VOCAB = (SMEM_LIMIT - FIXED_BYTES) / 4 - 8;
 
 __constant__ double c_exp_tab[NS_EXP_N] = {NS_EXP_TAB_VALUES};
+// the same table in global memory: a lookup with a different index in every lane is one L1 access there, but up to 32
+// serialised passes through the constant cache
+__device__ const double g_exp_tab[NS_EXP_N] = {NS_EXP_TAB_VALUES};
 
 // ------------------------------------------------------------------------------------
 // block-wide reductions, bit-deterministic: xor-butterfly inside the warp (commutative,

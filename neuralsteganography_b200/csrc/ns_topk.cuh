@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __
       if (r < K) {
         double x = (double)fmaxf(me.key, clamp_key);         // (double(x)/temp) - (double(max)/temp), :128-130
         if (!UNIT_TEMP) x = __ddiv_rn(x, P.temp);
-        es[r] = ns_exp64_core(x - dm, c_exp_tab);
+        es[r] = ns_exp64_core(x - dm, g_exp_tab);           // (table in global memory: every lane its own index)
         sid[r] = me.id;
         if (r == K - 1) sc.kth_key = me.key;
       }
