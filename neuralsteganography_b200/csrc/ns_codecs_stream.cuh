@@ -20,6 +20,18 @@
 // Same integers as the row-resident kernels: selection by (key, lower id first).
 // Serves: Huffman with bits_per_word <= 5 (n <= 32 group maxima), rank without top_p / min_prob (top_k clamps the count).
 
+// CTAs per SM the register budget is cut for, measured (profiles/r2b_experiments.txt, 14): the kernels are bound by how
+// many rows an SM has in flight, not by loads in flight per thread -- rank 4 (32 registers), Huffman 3 (40 registers),
+// four chunk loads in flight on the HBM sweep (was: 2 CTAs, 8 loads)
+#ifndef NSC_RANK_CTAS
+#define NSC_RANK_CTAS 4
+#endif
+#ifndef NSC_HUF_CTAS
+#define NSC_HUF_CTAS 3
+#endif
+#ifndef NSC_D1
+#define NSC_D1 4
+#endif
 constexpr int CT = 512;                      // threads per CTA
 constexpr int CW = CT / 32;
 constexpr int C_NB = 2048;                   // histogram buckets
@@ -76,7 +88,7 @@ __device__ __forceinline__ bool huf_build_warp(HufNode* nd, int n, int lane) {
 
 static_assert(C_GROUPS == 32 && C_GL * C_GROUPS == CT && C_GL <= 32 && 32 % C_GL == 0, "one group maximum per lane of a warp");
 template <int KIND>
-__global__ void __launch_bounds__(CT, 2) codec_stream_kernel(ns_codec_params P) {
+__global__ void __launch_bounds__(CT, (KIND == K_RANK_ENC || KIND == K_RANK_DEC) ? NSC_RANK_CTAS : NSC_HUF_CTAS) codec_stream_kernel(ns_codec_params P) {
   constexpr bool RANK = KIND == K_RANK_ENC || KIND == K_RANK_DEC;
   constexpr bool DECODE = KIND == K_RANK_DEC || KIND == K_HUF_DEC;
   constexpr bool USE_MASK = !RANK;                           // the baselines forbid two tokens, the rank codec none
@@ -220,7 +232,7 @@ __global__ void __launch_bounds__(CT, 2) codec_stream_kernel(ns_codec_params P) 
         }
       }
     }
-  }, Depth<8>());   // from HBM: more bytes in flight
+  }, Depth<NSC_D1>());   // from HBM: more bytes in flight
   {
     const unsigned gmask = ((1u << C_GL) - 1u) << (C_GL * (lane / C_GL));       // this lane's group of C_GL lanes
     const uint32_t a = __reduce_max_sync(gmask, ns_f32_orderable(bk));
