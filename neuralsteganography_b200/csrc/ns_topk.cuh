@@ -23,11 +23,20 @@
 
 constexpr int KT = 512;                      // threads per CTA
 constexpr int KW = KT / 32;
-constexpr int K_NB = 2048;                   // histogram buckets
+#ifndef NST_NB
+#define NST_NB 2048
+#endif
+#ifndef NST_TOPK_CAP
+#define NST_TOPK_CAP 384
+#endif
+constexpr int K_NB = NST_NB;                 // histogram buckets
 constexpr int K_BPT = K_NB / KT;
-constexpr int K_CAP = 1536;                  // candidates (keys >= k_c)
+#ifndef NST_CAP
+#define NST_CAP 1536
+#endif
+constexpr int K_CAP = NST_CAP;               // candidates (keys >= k_c)
 constexpr int K_HCAP = 2048;                 // chunks holding a candidate
-constexpr int K_TOPK_CAP = 384;              // one thread per kept token; 2.5 topk + 64 stays well below K_CAP
+constexpr int K_TOPK_CAP = NST_TOPK_CAP;              // one thread per kept token; 2.5 topk + 64 stays well below K_CAP
 constexpr int K_MIN_VOCAB = 8192;            // the sample needs 1024 distinct interior chunks
 #ifndef NST_U
 #define NST_U 4
@@ -44,7 +53,7 @@ constexpr float K_BAND_EPS = 0.0009765625f;  // the guard band of the throughput
 static_assert(K_TOPK_CAP <= KT && K_TOPK_CAP * 12 <= K_CAP * 8, "chain arrays live in the candidate / list areas");
 static_assert(K_HCAP * 4 <= K_CAP * 8, "the hit list lives in the list area");
 static_assert(K_U >= 1 && K_U <= 8, "hit entries carry K_U mask bits under the chunk index");
-static_assert(5 * K_TOPK_CAP / 2 + 64 + 400 <= K_CAP, "room for the spread of the candidate count");
+static_assert(5 * K_TOPK_CAP / 2 + 64 + 350 <= K_CAP, "room for the spread of the candidate count");
 
 // shapes the sweep kernel takes: the sample selection needs its rank within K_JMAX rounds
 inline bool k_shape_ok(int V, int K) {
