@@ -41,6 +41,9 @@ constexpr int K_MIN_VOCAB = 8192;            // the sample needs 1024 distinct i
 #ifndef NST_U
 #define NST_U 4
 #endif
+#ifndef NST_HINTS
+#define NST_HINTS 1
+#endif
 #ifndef NST_MIN_CTAS
 #define NST_MIN_CTAS 4
 #endif
@@ -100,6 +103,22 @@ __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __
   const int mk0 = (P.mask_id[0] >= 0 && P.mask_id[0] < V) ? P.mask_id[0] : -8;
   const int mk1 = (P.mask_id[1] >= 0 && P.mask_id[1] < V) ? P.mask_id[1] : -8;
   const int mc0 = (mk0 + mis) >> 2, mc1 = (mk1 + mis) >> 2;
+#if NST_HINTS
+  // L2 eviction hints: the sweep's lines may leave first, the sample's (read again by the sweep) stay.  The policy is made
+  // at run time from a fraction the compiler cannot fold -- a compile-time policy is rebuilt in every loop iteration.
+  u64 pol_last, pol_first;
+  {
+    const float one = __uint_as_float(0x3f800000u | ((uint32_t)P.B >> 31));      // 1.0f (B >= 0)
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, %1;" : "=l"(pol_last) : "f"(one));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, %1;" : "=l"(pol_first) : "f"(one));
+  }
+  auto ldg4 = [&](int c, bool last) -> float4 {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(g4 + c), "l"(last ? pol_first : pol_last));
+    return v;
+  };
+#else
   // (no L2 eviction hints: a policy operand costs the sweep loop a descriptor set-up per load, and the few chunks
   // that are read twice -- the sample, the hit chunks -- come back from L2 within microseconds anyway)
   auto ldg4 = [&](int c, bool) -> float4 {
@@ -108,6 +127,7 @@ __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(g4 + c));
     return v;
   };
+#endif
   // slot counter in shared memory, one plain atomic per calling thread (the compiler's warp-aggregated form of
   // atomicAdd costs twenty instructions on a path nearly every warp takes for two or three of its lanes)
   auto take_slot = [&](int* counter) -> int {
