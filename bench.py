@@ -416,11 +416,36 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
         tms = k0.elapsed_time(k1)
         ttps = B * tn / (tms * 1e-3)
+        # decode of the same cover tokens, and the round trip on a subset of the streams
+        tdec = ArithmeticStreams(B, V, precision=PRECISION, temp=0.9, topk=300, token_cap=K + W + 8, device=dev)
+        tdec.set_token_tensor(tk.tokens.clone(), tk.ntok.clone())
+        for t in range(W):
+            tdec.decode_step(pool[t % POOL])
+        torch.cuda.synchronize()
+        k0.record()
+        for t in range(tn):
+            tdec.decode_step(pool[(W + t) % POOL])
+        k1.record()
+        torch.cuda.synchronize()
+        tdms = k0.elapsed_time(k1)
+        tgot = tdec.out_bits.cpu().numpy().view(np.uint32)
+        tolen = tdec.out_len.cpu().numpy()
+        tcur = tk.cursor.cpu().numpy()
+        trt = True
+        for r in range(0, B, max(1, B // 64)):
+            n = int(min(tcur[r], tolen[r]))
+            full, rem = n // 32, n % 32
+            trt &= bool(np.array_equal(tgot[r, :full], words[r, :full]))
+            if rem:
+                trt &= bool((tgot[r, full] >> (32 - rem)) == (words[r, full] >> (32 - rem)))
         topk_leg = {"workload": "same pool, temp 0.9, precision 26, topk 300", "tokens_per_sec": ttps,
+                    "decode_tokens_per_sec": B * tn / (tdms * 1e-3), "roundtrip_ok": trt,
                     "bits_per_token": (int(tk.cursor.sum().item()) - c0) / (B * tn),
                     "roofline_frac": ttps * ALGO_BYTES_PER_TOKEN / 1e9 / peaks()[0], "steps": tn,
+                    "kernel": "ac_topk_stream_kernel (csrc/ns_topk.cuh: the row is read once), then ac_fast_kernel on the rows it leaves",
+                    "rows_left_to_row_resident_kernel": int(((tk.status & 16) != 0).sum().item()),
                     "rows_handed_to_exact_kernel": int(((tk.status & 4) != 0).sum().item())}
-        del tk
+        del tk, tdec
 
     # final gather of the cover tokens (the only collective; outside the hot path)
     gather_ms = None
