@@ -21,7 +21,10 @@
 // Rows this kernel does not carry (not certainly in rank form, too few / too many candidates, degenerate ties,
 // finish_sent tail) are queued in `mid` = {count, done, rows...}; ac_fast_kernel then runs on that list.
 
-constexpr int KT = 512;                      // threads per CTA
+#ifndef NST_KT
+#define NST_KT 512
+#endif
+constexpr int KT = NST_KT;                   // threads per CTA (512, or 256 with two ranks per thread in the chain)
 constexpr int KW = KT / 32;
 #ifndef NST_NB
 #define NST_NB 2048
@@ -53,18 +56,18 @@ constexpr int K_JMAX = 8;                    // rounds of the sample selection (
 constexpr int K_TIE_CAP = 256;               // keys in the boundary bucket (the order inside a bucket is quadratic)
 constexpr float K_MAGIC = 2097152.0f;        // 2^21: a float counts quarters there
 constexpr float K_BAND_EPS = 0.0009765625f;  // the guard band of the throughput kernels (F_BAND_EPS)
-static_assert(K_TOPK_CAP <= KT && K_TOPK_CAP * 12 <= K_CAP * 8, "chain arrays live in the candidate / list areas");
+static_assert(K_TOPK_CAP <= 2 * KT && K_TOPK_CAP * 12 <= K_CAP * 8, "chain arrays live in the candidate / list areas");
 static_assert(K_HCAP * 4 <= K_CAP * 8, "the hit list lives in the list area");
 static_assert(K_U >= 1 && K_U <= 8, "hit entries carry K_U mask bits under the chunk index");
 static_assert(5 * K_TOPK_CAP / 2 + 64 + 350 <= K_CAP, "room for the spread of the candidate count");
 
 // shapes the sweep kernel takes: the sample selection needs its rank within K_JMAX rounds
 inline bool k_shape_ok(int V, int K) {
-  return V >= K_MIN_VOCAB && K >= 2 && K <= K_TOPK_CAP && (long long)((5 * K) / 2 + 64) * 256 + V / 2 < (long long)(K_JMAX + 1) * V;
+  return V >= K_MIN_VOCAB && K >= 2 && K <= K_TOPK_CAP && (long long)((5 * K) / 2 + 64) * 256 + V / 2 < (long long)(K_JMAX + 1) * V;   // (256 sample keys per warp)
 }
 struct KCand { float key; int id; };
 struct KScal {
-  u64 red[KW];
+  u64 red[KW > 16 ? KW : 16];                  // one per warp (scan) / per group of 32 ranks (chain)
   uint32_t wmax[KW], smax[KW], smin[KW];
   float wsum[KW];
   int sel_bin, res_idx, res_found, nhit, ncand;
@@ -184,7 +187,7 @@ __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __
   float k_c, ref;
   {
     const int NI = W4 - 2;                                   // interior chunks 1 .. W4-2 (>= 2 KT: K_MIN_VOCAB)
-    const int cs0 = 1 + (int)(((long long)tid * NI) >> 10), cs1 = 1 + (int)(((long long)(tid + KT) * NI) >> 10);
+    const int cs0 = 1 + (int)(((long long)tid * NI) / (2 * KT)), cs1 = 1 + (int)(((long long)(tid + KT) * NI) / (2 * KT));
     float4 a = ldg4(cs0, false), b = ldg4(cs1, false);
     // ---- the stream's scalars: three threads of three warps (loads issued together, behind the sample loads), handed
     // on through shared memory at the first barrier
@@ -397,43 +400,69 @@ __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __
     if (tid == 0) k_defer(P, mid, row);
     return;
   }
-  // ---- bin widths, prefix sums, overfill, selection: thread r holds the token of rank r; only the warps that hold a
-  // rank go on (named barrier over those warps)
-  const int nwt = ((K + 31) >> 5) << 5;                      // threads of the warps holding a rank
+  // ---- bin widths, prefix sums, overfill, selection: thread t holds the tokens of rank t + s KT (s < RPT); only the
+  // warps that hold a rank go on (named barrier over those warps).  Groups of 32 consecutive ranks are reduced by one
+  // warp each and combined in rank order: the reduction order of fast_rank_row, whatever KT is.
+  constexpr int RPT = (K_TOPK_CAP + KT - 1) / KT;            // ranks per thread
+  static_assert(RPT * KW <= (KW > 16 ? KW : 16), "one reduction slot per group of 32 ranks");
+  const int NG = (K + 31) >> 5;                              // groups that hold a rank
+  const int nwt = NG * 32 < KT ? NG * 32 : KT;               // threads of the warps holding a rank
   if (tid >= nwt) return;
   auto tail_sync = [&]() { asm volatile("bar.sync 1, %0;" :: "r"(nwt) : "memory"); };
-  const int NWK = nwt >> 5;
   const u64 lo = sc.lo, R = sc.R;
-  const double ev = tid < K ? es[tid] : 0.0;
-  double S = ev;                                             // sum of the kept e, fixed order (:146)
+  double ev[RPT];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) S = S + __shfl_xor_sync(0xffffffffu, S, o);
-  if (lane == 0) sc.red[warp] = (u64)__double_as_longlong(S);
+  for (int s = 0; s < RPT; ++s) {
+    const int r = tid + s * KT;
+    ev[s] = r < K ? es[r] : 0.0;
+    double S = ev[s];                                        // sum of the kept e, fixed order (:146)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) S = S + __shfl_xor_sync(0xffffffffu, S, o);
+    if (lane == 0) sc.red[warp + s * KW] = (u64)__double_as_longlong(S);
+  }
   tail_sync();
-  S = __longlong_as_double((long long)sc.red[0]);
-  for (int w = 1; w < NWK; ++w) S = S + __longlong_as_double((long long)sc.red[w]);   // warps without a rank add 0.0: same bits as all KW
+  double S = __longlong_as_double((long long)sc.red[0]);
+  for (int g = 1; g < NG; ++g) S = S + __longlong_as_double((long long)sc.red[g]);   // groups without a rank would add 0.0: same bits
   const double C = __ddiv_rn((double)R, S);
-  const u64 q = tid < K ? (u64)__double2ll_rn(ev * C) : 0ull;   // :146-149
-  u64 cum = q;                                               // inclusive prefix sums over the ranks (:150)
+  u64 cum[RPT];
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const u64 t = __shfl_up_sync(0xffffffffu, cum, o); if (lane >= o) cum += t; }
+  for (int s = 0; s < RPT; ++s) {
+    const int r = tid + s * KT;
+    cum[s] = r < K ? (u64)__double2ll_rn(ev[s] * C) : 0ull;  // :146-149; inclusive prefix sums over the ranks (:150)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u64 t = __shfl_up_sync(0xffffffffu, cum[s], o); if (lane >= o) cum[s] += t; }
+  }
   tail_sync();                                               // red of the sum is consumed
-  if (lane == 31) sc.red[warp] = cum;
+#pragma unroll
+  for (int s = 0; s < RPT; ++s) if (lane == 31) sc.red[warp + s * KW] = cum[s];
   tail_sync();
   u64 Q = 0;
   {
-    u64 wo = 0;
-    for (int w = 0; w < NWK; ++w) { const u64 x = sc.red[w]; if (w < warp) wo += x; Q += x; }
-    cum += wo;
+    u64 wo[RPT];
+#pragma unroll
+    for (int s = 0; s < RPT; ++s) wo[s] = 0;
+    for (int g = 0; g < NG; ++g) {
+      const u64 x = sc.red[g];
+#pragma unroll
+      for (int s = 0; s < RPT; ++s) if (g < warp + s * KW) wo[s] += x;
+      Q += x;
+    }
+#pragma unroll
+    for (int s = 0; s < RPT; ++s) cum[s] += wo[s];
   }
   u64* cums = reinterpret_cast<u64*>(list);                  // [K_TOPK_CAP]; the gathered list is no longer needed
-  if (tid < K) cums[tid] = cum;
+#pragma unroll
+  for (int s = 0; s < RPT; ++s) if (tid + s * KT < K) cums[tid + s * KT] = cum[s];
   tail_sync();
   // overfill (:153-158): drop the ranks from the first prefix sum above the range on
   int kk = K;
   u64 slack;
   if (Q > R) {
-    if (tid < K && cum > R && (tid == 0 || cums[tid - 1] <= R)) sc.res_idx = tid;
+#pragma unroll
+    for (int s = 0; s < RPT; ++s) {
+      const int r = tid + s * KT;
+      if (r < K && cum[s] > R && (r == 0 || cums[r - 1] <= R)) sc.res_idx = r;
+    }
     tail_sync();
     kk = sc.res_idx;
     slack = R - (kk > 0 ? cums[kk - 1] : 0ull);
@@ -444,24 +473,38 @@ __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __
     slack = R - Q;
   }
   // bin of rank r: [cums[r-1] + slack, cums[r] + slack), rank 0 starts at 0 and absorbs the slack (:158)
-  const u64 my_lo = (tid > 0 && tid < K) ? cums[tid - 1] + slack : 0ull;
-  const u64 my_hi = cum + slack;
+  u64 my_lo[RPT], my_hi[RPT];
+#pragma unroll
+  for (int s = 0; s < RPT; ++s) {
+    const int r = tid + s * KT;
+    my_lo[s] = (r > 0 && r < K) ? cums[r - 1] + slack : 0ull;
+    my_hi[s] = cum[s] + slack;
+  }
   if (MODE == MODE_ENC) {
     const u64 m_rel = sc.window - lo;                        // next `precision` message bits (:168-171)
-    if (tid < kk && my_lo <= m_rel && m_rel < my_hi) sc.res_idx = tid;   // :172 (empty bins never match)
+#pragma unroll
+    for (int s = 0; s < RPT; ++s)
+      if (tid + s * KT < kk && my_lo[s] <= m_rel && m_rel < my_hi[s]) sc.res_idx = tid + s * KT;   // :172 (empty bins never match)
     tail_sync();
     const int r = sc.res_idx;
-    if (tid == (r < kk ? r : 0)) {
-      if (r >= kk && P.status) atomicOr(&P.status[row], NS_ST_BIN_OVERFLOW);   // cannot happen: the bins tile the range
-      finish_encode(P, row, sc.slot, sid[tid], lo + my_lo, lo + my_hi, (u64)K, Q, sc.cursor, sc.mlen);   // :175-176
-    }
+    const int rr = r < kk ? r : 0;
+#pragma unroll
+    for (int s = 0; s < RPT; ++s)
+      if (tid + s * KT == rr) {
+        if (r >= kk && P.status) atomicOr(&P.status[row], NS_ST_BIN_OVERFLOW);   // cannot happen: the bins tile the range
+        finish_encode(P, row, sc.slot, sid[rr], lo + my_lo[s], lo + my_hi[s], (u64)K, Q, sc.cursor, sc.mlen);   // :175-176
+      }
   } else {
     const int tok = sc.tok;
     const bool tok_ok = tok >= 0 && tok < V;
-    if (tid < kk && tok_ok && sid[tid] == tok) { sc.res_idx = tid; sc.res_found = 1; }
+#pragma unroll
+    for (int s = 0; s < RPT; ++s)
+      if (tid + s * KT < kk && tok_ok && sid[tid + s * KT] == tok) { sc.res_idx = tid + s * KT; sc.res_found = 1; }
     tail_sync();
     const bool in_range = sc.res_found != 0;
     const int r = in_range ? sc.res_idx : 0;                 // :342 / :347-348: unknown tokens are coded as rank 0
-    if (tid == r) finish_decode(P, row, sc.slot, in_range || !tok_ok, lo + my_lo, lo + my_hi, (u64)K, Q);
+#pragma unroll
+    for (int s = 0; s < RPT; ++s)
+      if (tid + s * KT == r) finish_decode(P, row, sc.slot, in_range || !tok_ok, lo + my_lo[s], lo + my_hi[s], (u64)K, Q);
   }
 }
