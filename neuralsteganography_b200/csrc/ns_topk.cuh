@@ -59,6 +59,7 @@ constexpr float K_BAND_EPS = 0.0009765625f;  // the guard band of the throughput
 static_assert(K_TOPK_CAP <= 2 * KT && K_TOPK_CAP * 12 <= K_CAP * 8, "chain arrays live in the candidate / list areas");
 static_assert(K_HCAP * 4 <= K_CAP * 8, "the hit list lives in the list area");
 static_assert(K_U >= 1 && K_U <= 8, "hit entries carry K_U mask bits under the chunk index");
+static_assert(KT >= 256 && (KT & (KT - 1)) == 0, "chunk ownership by mask; three warps of helpers beside the gathering ones");
 static_assert(5 * K_TOPK_CAP / 2 + 64 + 350 <= K_CAP, "room for the spread of the candidate count");
 
 // shapes the sweep kernel takes: the sample selection needs its rank within K_JMAX rounds
@@ -75,7 +76,7 @@ struct KScal {
   float kth_key;
   // the stream's scalars (thread 0) and the row's constants (one thread, while the others gather)
   u64 lo, R, window;
-  double dm, thr;
+  double dm;
   float M, kappa_r, clamp_key, scale2, boff2;
   int go, slot, cursor, mlen, tok, bad, bad2;
 };
@@ -190,7 +191,9 @@ __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __
     const int cs0 = 1 + (int)(((long long)tid * NI) / (2 * KT)), cs1 = 1 + (int)(((long long)(tid + KT) * NI) / (2 * KT));
     float4 a = ldg4(cs0, false), b = ldg4(cs1, false);
     // ---- the stream's scalars: three threads of three warps (loads issued together, behind the sample loads), handed
-    // on through shared memory at the first barrier
+    // on through shared memory at the first barrier.  Only what decides whether the row is coded and where its state
+    // lies is fetched here; what depends on it (message window, observed token, 1/range) is fetched while the
+    // candidates are gathered, by warps that do not gather
     if (tid == 0) {                                          // may the row be coded at all; slot, observed token
       const int ph0 = P.phase ? (int)P.phase[row] : NS_PHASE_CODING;
       const int slot = P.ntok ? P.ntok[row] : 0;
@@ -213,16 +216,12 @@ __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __
         go = 0;
       }
       sc.go = go; sc.slot = slot;
-      if (go && MODE != MODE_ENC) sc.tok = P.token_in[(size_t)row * P.token_stride + slot];
       sc.nhit = 0; sc.ncand = 0; sc.kth_key = -INFINITY;
     } else if (tid == 32) {                                  // the interval
       const u64 lo = P.lo[row], R = P.hi[row] - lo;          // arithmetic.py:140
       sc.lo = lo; sc.R = R;
-      sc.thr = __ddiv_rn(1.0, (double)R);                    // :141
-    } else if (tid == 64 && MODE == MODE_ENC) {              // the next `precision` message bits
-      const int cursor = P.cursor[row], mlen = P.msg_len[row];
-      sc.cursor = cursor; sc.mlen = mlen;
-      sc.window = ns_read_bits(P.msg + (size_t)row * P.msg_stride, cursor, mlen, P.precision);   // :168-171
+    } else if (tid == 64 && MODE == MODE_ENC) {              // where the message stands
+      sc.cursor = P.cursor[row]; sc.mlen = P.msg_len[row];
     }
     a = fold(a, cs0); b = fold(b, cs1);
     // j-th largest of the warp's 256 sample keys (ties struck out together), j ~ (2.5 K + 64) 256 / V: about
@@ -299,7 +298,9 @@ __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __
     if (lane == 0) { sc.wmax[warp] = wk; sc.wsum[warp] = wts; }
   }
   __syncthreads();                                           // the hit list and the warps' maxima / sums are complete
-  // ---- row constants: two threads of two warps (the formulas of fast_row, with the bound in place of the estimate) ...
+  // ---- row constants and the stream's dependent scalars: three threads of the last three warps (the formulas of
+  // fast_row, with the bound in place of the estimate) ...
+  constexpr int K_GT = KT - 96;                              // threads that gather meanwhile
   if (tid == KT - 32) {                                      // bound of the normaliser -> key above which p >= 1/R for certain
     uint32_t mk = 0;
     float tot = 0.f;
@@ -308,10 +309,12 @@ __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __
     const float M = key_of_pack((u64)mk << 32);
     const float ssum = 4.0f * tot * k_ex2((ref - M) * c2);   // >= sum_j exp((x_j - M)/temp): four keys per chunk, each <= its maximum
     const float tf = (float)P.temp;
-    const float key_th = fmaf(tf * 0.6931471805599453f, __log2f((float)(sc.thr * (double)ssum)), M);   // p >= 1/R <= key >= M + temp ln(bound / R)
+    const u64 R = sc.R;
+    const double thr = __ddiv_rn(1.0, (double)R);            // :141
+    const float key_th = fmaf(tf * 0.6931471805599453f, __log2f((float)(thr * (double)ssum)), M);   // p >= 1/R <= key >= M + temp ln(bound / R)
     const float clamp_key = (float)((double)M - 700.0 * P.temp);
     sc.kappa_r = key_th + tf * K_BAND_EPS + 0.02f * tf;      // guard for the fp32 arithmetic of the bound
-    sc.bad = (!(ssum > 0.0f) || !(ssum < 3.0e38f) || !(sc.R >= 2) || !(key_th > clamp_key) || !(M > -3.0e38f) || !(M < 3.0e38f)) ? 1 : 0;
+    sc.bad = (!(ssum > 0.0f) || !(ssum < 3.0e38f) || !(R >= 2) || !(key_th > clamp_key) || !(M > -3.0e38f) || !(M < 3.0e38f)) ? 1 : 0;
   } else if (tid == KT - 64) {                               // maximum -> bucket function of the candidates, exponent offset
     uint32_t mk = 0;
 #pragma unroll
@@ -325,11 +328,14 @@ __global__ void __launch_bounds__(KT, K_MIN_CTAS) ac_topk_stream_kernel(const __
     sc.clamp_key = (float)(Md - 700.0 * P.temp);
     sc.scale2 = scale2; sc.boff2 = boff2;
     sc.bad2 = (!(M > k_c) || !(scale2 > 0.0f) || !(scale2 < 3.0e38f) || !(fabsf(boff2) < 3.0e38f)) ? 1 : 0;
+  } else if (tid == KT - 96) {                               // the next `precision` message bits (:168-171) / the observed token
+    if (MODE == MODE_ENC) sc.window = ns_read_bits(P.msg + (size_t)row * P.msg_stride, sc.cursor, sc.mlen, P.precision);
+    else sc.tok = P.token_in[(size_t)row * P.token_stride + sc.slot];
   }
-  // ---- ... while the others gather (L2) the candidates = keys >= k_c of the hit chunks
-  {
+  // ---- ... while the other warps gather (L2) the candidates = keys >= k_c of the hit chunks
+  if (tid < K_GT) {
     const int nhit = min(sc.nhit, K_HCAP);
-    for (int h = tid; h < nhit; h += KT) {
+    for (int h = tid; h < nhit; h += K_GT) {
       const uint32_t ent = (uint32_t)hits[h];
       for (uint32_t hm = ent & ((1u << K_U) - 1u); hm != 0; hm &= hm - 1u) {
         const int c = (int)(ent >> K_U) + (__ffs((int)hm) - 1) * KT, b0 = 4 * c - mis;
