@@ -5,13 +5,16 @@
 // nothing below them matters: no fp64 work on the row at all, and the row is read from HBM exactly ONCE with a
 // dozen instructions per 16-byte chunk.  One 512-thread CTA per row, 33 KB of shared memory, four CTAs per SM,
 // so the chain of one row hides under the sweeps of the others.
-//   sample   two chunks per thread (4096 logits, strided over the row): count histogram of the sample -> a key
-//            bound k_c that about 2.5 topk + 64 keys of the row exceed (order statistics of the sample: the
-//            count above the r-th largest sample key has relative spread 1/sqrt(r))
+//   sample   two chunks per thread (4096 logits, strided over the row): every warp takes the j-th largest of its 256
+//            sample keys (j rounds of warp maximum + strike-out), the mean over the warps is a key bound k_c that about
+//            2.5 topk + 64 keys of the row exceed (order statistics: relative spread 1/sqrt(16 j)).  Three threads of
+//            three warps fetch what decides whether the row is coded (phase, slot, interval, message cursor) meanwhile
 //   sweep    (HBM, once) per chunk: its maximum m -> row maximum M, an UPPER bound 4 sum_chunks exp((m - M)/temp)
 //            of the softmax normaliser (one ex2 per chunk), and the chunk index to a hit list when m >= k_c
 //   gather   the hit chunks again (L2): the keys >= k_c, the candidates; at least topk of them means the topk
-//            largest keys of the row are the topk largest candidates (ties included: equal keys are candidates too)
+//            largest keys of the row are the topk largest candidates (ties included: equal keys are candidates too).
+//            The last three warps do not gather: one thread each derives the row constants (two of them) and fetches
+//            the message window / the observed token
 //   order    count histogram of the candidates over [k_c, M] -> grouped by bucket -> exact order inside each bucket
 //            (key, lower id first) -> rank of every candidate; the row is certainly in rank form when the key of rank
 //            topk-1 has p >= 1/range even against the upper bound of the normaliser (plus the guard band)
