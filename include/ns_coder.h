@@ -114,9 +114,9 @@ typedef struct ns_ac_params {
      Requesting them routes the step through the exact kernel. */
   double* stats;
   /* Optional second work queue, B+2 int32 zeroed once by the caller (same layout as slow_ws).  When given, a step whose
-     top-k binds (2 <= topk <= 384, V >= 8192 and V >= 32 (2.5 topk + 64)) starts with the sweep kernel of the rank form
+     top-k binds (2 <= topk <= 512, V >= 8192 and V >= 32 (2.5 topk + 64)) starts with the sweep kernel of the rank form
      (csrc/ns_topk.cuh: the row is read once, no resident row, four rows per SM); rows it does not carry are queued here
-     and done by the row-resident kernel (csrc/ns_fast.cuh), which also serves every other shape with topk <= 512.
+     and done by the row-resident kernel (csrc/ns_fast.cuh), which also serves the smaller vocabularies.
      NULL = row-resident kernel for every row.  Results are identical. */
   int32_t* rank_ws;
   /* Reserved; must be 0. */

@@ -3,7 +3,7 @@
 //
 // When at least topk tokens have p >= 1/range the kept set is the topk largest logits (arithmetic.py:142) and
 // nothing below them matters: no fp64 work on the row at all, and the row is read from HBM exactly ONCE with a
-// dozen instructions per 16-byte chunk.  One 512-thread CTA per row, 33 KB of shared memory, four CTAs per SM,
+// dozen instructions per 16-byte chunk.  One 512-thread CTA per row, 37 KB of shared memory, four CTAs per SM,
 // so the chain of one row hides under the sweeps of the others.
 //   sample   two chunks per thread (4096 logits, strided over the row): every warp takes the j-th largest of its 256
 //            sample keys (j rounds of warp maximum + strike-out), the mean over the warps is a key bound k_c that about
@@ -33,12 +33,12 @@ constexpr int KW = KT / 32;
 #define NST_NB 2048
 #endif
 #ifndef NST_TOPK_CAP
-#define NST_TOPK_CAP 384
+#define NST_TOPK_CAP 512
 #endif
 constexpr int K_NB = NST_NB;                 // histogram buckets
 constexpr int K_BPT = K_NB / KT;
 #ifndef NST_CAP
-#define NST_CAP 1536
+#define NST_CAP 1792
 #endif
 constexpr int K_CAP = NST_CAP;               // candidates (keys >= k_c)
 constexpr int K_HCAP = 2048;                 // chunks holding a candidate

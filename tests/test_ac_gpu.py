@@ -255,7 +255,7 @@ def test_device_statistics_match_oracle():
     (42001, 26, 300, 1.0, 8.0, 0.0),      # peaked rows: often fewer than topk tokens above the cutoff
     (50257, 26, 64, 1.0, 3.0, 0.25),      # quantised logits: many exact ties across the top-k boundary
     (5000, 20, 100, 1.0, 2.0, 0.5),       # small vocabulary, dense ties (boundary bucket overflow -> hand-over)
-    (42001, 26, 384, 0.8, 4.0, 0.0),      # largest top-k of the sweep kernel (385 .. 512: the row-resident kernel alone)
+    (42001, 26, 384, 0.8, 4.0, 0.0),      # a top-k between the usual one and the largest of the path
     (9000, 20, 10, 1.0, 2.0, 0.0),        # smallest vocabularies of the sweep kernel (three rounds of the sample selection)
     (50257, 16, 300, 0.9, 6.0, 0.0),      # top-k rarely binds at this range: the sweep kernel leaves the rows to the threshold form
 ])
