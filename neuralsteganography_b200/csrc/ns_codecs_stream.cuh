@@ -96,24 +96,6 @@ __global__ void __launch_bounds__(CT, (KIND == K_RANK_ENC || KIND == K_RANK_DEC)
   __shared__ ListEntry list[C_LIST];
   __shared__ StreamScal sc;
   const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, V = P.V;
-  // ---- the stream's scalars
-  const uint8_t phase = P.phase ? P.phase[row] : (uint8_t)NS_PHASE_CODING;
-  const int slot = P.ntok ? P.ntok[row] : 0;
-  if (phase == NS_PHASE_DONE) return;
-  if (!DECODE && P.ntok && slot >= P.token_cap) {
-    if (tid == 0) { if (P.phase) P.phase[row] = NS_PHASE_DONE; if (P.status) atomicOr(&P.status[row], NS_ST_TOKEN_OVERFLOW); }
-    return;
-  }
-  const int total = (DECODE && P.ntok_total) ? P.ntok_total[row] : 0x7fffffff;
-  if (DECODE && slot >= total) { if (tid == 0 && P.phase) P.phase[row] = NS_PHASE_DONE; return; }
-  int cursor = 0, mlen = 0, tok = -1;
-  uint32_t window = 0;
-  if (!DECODE) {
-    cursor = P.cursor[row]; mlen = P.msg_len[row];
-    window = (uint32_t)ns_read_bits(P.msg + (size_t)row * P.msg_stride, cursor, mlen, 32);
-  } else {
-    tok = P.token_in[(size_t)row * P.token_stride + slot];
-  }
   const float* g = P.logits + (size_t)row * (size_t)P.ld;
   const int mis = (int)(((uintptr_t)g & 15u) >> 2);
   const int W4 = (mis + V + 3) >> 2;
@@ -132,6 +114,30 @@ __global__ void __launch_bounds__(CT, (KIND == K_RANK_ENC || KIND == K_RANK_DEC)
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(g4 + c), "l"(last ? pol_first : pol_last));
     return v;
   };
+  // rank encode: the sample chunk of this thread is requested before the stream's scalars are fetched (three dependent
+  // loads), so that the row's first bytes are on their way while those resolve
+  const int s_stride = (W4 - 2) / CT > 0 ? (W4 - 2) / CT : 1;
+  const int s_cs = 1 + tid * s_stride;
+  float4 s_v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (RANK && !DECODE && s_cs < W4 - 1) s_v = ldg4(s_cs, false);
+  // ---- the stream's scalars
+  const uint8_t phase = P.phase ? P.phase[row] : (uint8_t)NS_PHASE_CODING;
+  const int slot = P.ntok ? P.ntok[row] : 0;
+  if (phase == NS_PHASE_DONE) return;
+  if (!DECODE && P.ntok && slot >= P.token_cap) {
+    if (tid == 0) { if (P.phase) P.phase[row] = NS_PHASE_DONE; if (P.status) atomicOr(&P.status[row], NS_ST_TOKEN_OVERFLOW); }
+    return;
+  }
+  const int total = (DECODE && P.ntok_total) ? P.ntok_total[row] : 0x7fffffff;
+  if (DECODE && slot >= total) { if (tid == 0 && P.phase) P.phase[row] = NS_PHASE_DONE; return; }
+  int cursor = 0, mlen = 0, tok = -1;
+  uint32_t window = 0;
+  if (!DECODE) {
+    cursor = P.cursor[row]; mlen = P.msg_len[row];
+    window = (uint32_t)ns_read_bits(P.msg + (size_t)row * P.msg_stride, cursor, mlen, 32);
+  } else {
+    tok = P.token_in[(size_t)row * P.token_stride + slot];
+  }
   auto fold = [&](float4 v, int c) -> float4 {               // -0 -> +0; forbidden tokens (huffman_baseline.py:26-27)
     if (RANK) return v;                                      // the rank codec compares floats (-0 == +0) and folds where it packs a key
     v.x += 0.0f; v.y += 0.0f; v.z += 0.0f; v.w += 0.0f;
@@ -176,10 +182,9 @@ __global__ void __launch_bounds__(CT, (KIND == K_RANK_ENC || KIND == K_RANK_DEC)
   float scale = 0.0f, boff = C_MAGIC;
   if (RANK && !DECODE) {
     float sb = -INFINITY, sl = INFINITY;
-    const int stride = (W4 - 2) / CT > 0 ? (W4 - 2) / CT : 1;
-    const int cs = 1 + tid * stride;
+    const int cs = s_cs;
     if (cs < W4 - 1) {
-      const float4 v = fold(ldg4(cs, false), cs);
+      const float4 v = fold(s_v, cs);
       sb = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
       sl = fminf(fminf(v.x > -1e9f ? v.x : INFINITY, v.y > -1e9f ? v.y : INFINITY),
                  fminf(v.z > -1e9f ? v.z : INFINITY, v.w > -1e9f ? v.w : INFINITY));
